@@ -1,0 +1,169 @@
+/*
+ * qfa_b200.h -- C ABI of libqfa_b200.so: the B200-native replacement for the hot
+ * path of ZechangSun/QFA (masked low-rank + diagonal Gaussian likelihood, its
+ * gradient, and the posterior continuum prediction).
+ *
+ * The reference has NO FFI (it is pure Python/PyTorch);
+ * the drop-in surface is the Python object API of QFA/model.py + QFA/optimizer.py.
+ * qfa_b200/model.py and qfa_b200/optimizer.py mirror that API and call the entry
+ * points below through ctypes with raw device pointers.  Each entry point names
+ * the reference code it replaces (paths relative to the reference repository).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host; buffers are
+ *    contiguous, row-major, 4-byte aligned (16-byte for the packed buffers); the
+ *    library allocates nothing that outlives a call and keeps no pointers.
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it.
+ *  - return value: 0 = ok; negative = argument/shape error found on the host
+ *    before any launch (see QFA_ERR_*); positive = cudaError_t.  Text of the last
+ *    error of the calling thread: qfa_last_error_string().  No exceptions cross.
+ *  - precision: QFA_PREC_FP64 computes everything in double and its T-typed
+ *    outputs are double; the other modes compute in float and T = float.
+ *  - Nh <= 32 (internally zero-padded to 4/8/16/32, which is exact).
+ */
+#ifndef QFA_B200_H
+#define QFA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QFA_ABI_VERSION 1
+
+/* precision modes */
+#define QFA_PREC_FP64 0 /* double everywhere; parity mode (<=1e-5 vs fp64-promoted reference) */
+#define QFA_PREC_FP32 1 /* float CUDA-core arithmetic (the reference itself is a float32 program) */
+#define QFA_PREC_TF32 2 /* "mixed": tcgen05 kind::tf32 Gram contractions, float elsewhere */
+
+/* mean optical depth laws, reference QFA/utils.py:95-141,149-171 (series = 1) */
+#define QFA_TAU_BECKER 0
+#define QFA_TAU_FG 1
+#define QFA_TAU_KAMBLE 2
+#define QFA_TAU_MOCK 3
+
+/* flags */
+#define QFA_FLAG_ZERO_ACC 1 /* qfa_train_accumulate: clear `acc` before accumulating */
+
+/* error codes (negative) */
+#define QFA_ERR_NULL -1
+#define QFA_ERR_SHAPE -2
+#define QFA_ERR_NH -3
+#define QFA_ERR_PRECISION -4
+#define QFA_ERR_WORKSPACE -5
+#define QFA_ERR_ALIGN -6
+#define QFA_ERR_LAW -7
+#define QFA_ERR_UNSUPPORTED -8
+
+/*
+ * Model view.  `params` is the packed float32 parameter buffer
+ *     [ F (Npix*Nh, row-major) | Psi (Npix) | omega (Nb) | tau0 | c0 | beta ]
+ * i.e. the six tensors of reference QFA.parameters (model.py:297-306) laid out
+ * back to back so that the optimiser update is one launch; Npix = Nb + Nr.
+ * `mu` (Npix floats) is only read by qfa_predict (reference model.py:166,180).
+ */
+typedef struct QfaModel {
+    int32_t Nb, Nr, Nh;
+    int32_t tau_law;
+    const float* params;
+    const float* mu;
+} QfaModel;
+
+int qfa_abi_version(void);
+const char* qfa_last_error_string(void);
+
+/* number of elements of the packed parameter buffer: Npix*Nh + Npix + Nb + 3 (reference model.py:42) */
+size_t qfa_param_len(int Nb, int Nr, int Nh);
+
+/*
+ * Accumulation buffer ("acc", element type T), the ONLY thing that has to be
+ * all-reduced (sum) between GPUs in data-parallel training:
+ *   [ sumF (Npix*Nh) | sumPsi (Npix) | sumOmega (Nb) | sum tau0,c0,beta (3) |
+ *     pixel counts (Npix) | scalar counts tau0,c0,beta (3) | sum NLL (1) | #spectra (1) |
+ *     sum dNLL/dmu (Npix)  (extra; not used by the reference-parity gradient) ]
+ */
+size_t qfa_acc_len(int Nb, int Nr, int Nh);
+size_t qfa_train_workspace_bytes(int Nb, int Nr, int Nh, int B, int precision);
+size_t qfa_predict_workspace_bytes(int Nb, int Nr, int Nh, int B, int precision);
+
+/*
+ * Replaces the per-spectrum loop of QFA.forward (model.py:98-103) and
+ * QFA.loglikelihood_and_gradient_for_single_spectra (model.py:107-158, with
+ * utils.py:12-54 MatrixInverse/MatrixLogDet and utils.py:57-92,95-171):
+ * adds, for the B spectra given, the per-spectrum partials and the non-zero
+ * counts into `acc`.  delta,error: (B,Npix) float; zabs: (B,Nb) float;
+ * mask: (B,Npix) bytes (torch.bool), non-zero = pixel is used.
+ * nll_per_spectrum: T[B] or NULL.
+ */
+int qfa_train_accumulate(const QfaModel* model, const float* delta, const float* error,
+                         const float* zabs, const uint8_t* mask, int B,
+                         void* workspace, size_t workspace_bytes,
+                         void* acc, void* nll_per_spectrum,
+                         int precision, int flags, void* stream);
+
+/*
+ * Replaces the tail of QFA.forward (model.py:100,104): loss = sum NLL / #spectra,
+ * grad[e] = sum[e] / count[e] (0/0 -> NaN exactly like the reference).
+ * grads: float[qfa_param_len] in the packed parameter layout; loss: float[1].
+ */
+int qfa_grads_finalize(const void* acc, int Nb, int Nr, int Nh, int precision,
+                       float* grads, float* loss, void* stream);
+
+/*
+ * Replaces QFA.prediction_for_single_spectra (model.py:160-180) for a batch.
+ * flux,error: (B,Npix) float; zabs (B,Nb); mask (B,Npix) bytes.
+ * Outputs (element type T; any of hmean/hcov/cont/unc may be NULL = not wanted,
+ * nll-only call = likelihood / out-of-distribution scoring):
+ *   nll (B) NEGATIVE log-likelihood, hmean (B,Nh), hcov (B,Nh,Nh),
+ *   cont (B,Npix) = mu + F hmean, unc (B,Npix) = sqrt(diag(F hcov F^T)).
+ */
+int qfa_predict(const QfaModel* model, const float* flux, const float* error,
+                const float* zabs, const uint8_t* mask, int B,
+                void* workspace, size_t workspace_bytes,
+                void* nll, void* hmean, void* hcov, void* cont, void* unc,
+                int precision, int flags, void* stream);
+
+/*
+ * Replaces Adam.update (optimizer.py:47-52) followed by the clipping setter
+ * QFA.parameters (model.py:308-316, 233-241), fused on the packed buffers and
+ * reading the gradient straight from `acc` (sum/count), so that
+ * forward -> all-reduce(acc) -> update needs no intermediate tensor.
+ * params, m, v: float[qfa_param_len], updated in place.
+ * bias1 = 1 - b1^(i+1), bias2 = 1 - b2^(i+1), lr = scheduled lr (optimizer.py:98),
+ * all evaluated on the host from the EPOCH counter i like the reference.
+ * If grads_in != NULL it is used instead of acc (float[qfa_param_len]).
+ */
+int qfa_adam_clip_step(float* params, float* m, float* v,
+                       const void* acc, const float* grads_in,
+                       int Nb, int Nr, int Nh, int precision,
+                       float lr, float b1, float b2, float eps, float weight_decay,
+                       float bias1, float bias2,
+                       float min_value, float max_value, void* stream);
+
+/* Replaces QFA.clip (model.py:233-241) on the packed parameter buffer. */
+int qfa_clip(float* params, int Nb, int Nr, int Nh, float min_value, float max_value, void* stream);
+
+/*
+ * Replaces QFA.smooth (model.py:243-252): box filters of width 15 (omega, Psi) and
+ * 31 (each column of F) that ignore out-of-range taps (count_include_pad=False).
+ * params_out must not alias params_in.
+ */
+int qfa_smooth(const float* params_in, float* params_out, int Nb, int Nr, int Nh, void* stream);
+
+/*
+ * Device-side data preparation (reference QFA/dataloader.py:102,135-136, Ly-alpha
+ * only -- exact on grids that start redward of Ly-beta such as the SDSS one):
+ *   zabs[b,i]  = (1+zqso[b]) * wav[i] / 1215.67 - 1            (i < Nb)
+ *   delta[b,i] = flux[b,i] - mu[i] * exp(-tau(zabs[b,i]))      (A = 1 for i >= Nb)
+ * wav: float[Npix] rest-frame grid; either output may be NULL.
+ */
+int qfa_prepare_batch(const float* flux, const float* zqso, const float* wav, const float* mu,
+                      int B, int Nb, int Nr, int tau_law,
+                      float* zabs_out, float* delta_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QFA_B200_H */

@@ -1,0 +1,452 @@
+// C ABI of libqfa_b200.so (see include/qfa_b200.h) + the small parameter-side kernels.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/qfa_b200.h"
+#include "qfa_kernels.cuh"
+
+using namespace qfa;
+
+// ---------------------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+#define CK(call)                                           \
+    do {                                                   \
+        cudaError_t e_ = (call);                           \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+extern "C" int qfa_abi_version(void) { return QFA_ABI_VERSION; }
+extern "C" const char* qfa_last_error_string(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------
+// layouts
+// ---------------------------------------------------------------------------------------
+extern "C" size_t qfa_param_len(int Nb, int Nr, int Nh) {
+    size_t P = (size_t)Nb + Nr;
+    return P * Nh + P + Nb + 3;
+}
+extern "C" size_t qfa_acc_len(int Nb, int Nr, int Nh) {
+    size_t P = (size_t)Nb + Nr;
+    return P * Nh + P + Nb + 3 + P + 3 + 1 + 1 + P;
+}
+static inline int pad_h(int Nh) { return Nh <= 4 ? 4 : Nh <= 8 ? 8 : Nh <= 16 ? 16 : 32; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline size_t tsize(int precision) { return precision == QFA_PREC_FP64 ? 8 : 4; }
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+// Spectra per sub-batch: sized so that one sub-batch of inputs stays L2-resident between the
+// spectrum-major pass and the pixel-major pass (B200: 126 MB L2).
+static int subbatch_size(int P, int Nb, int B) {
+    static long mb = -1;
+    if (mb < 0) {
+        const char* s = getenv("QFA_SUBBATCH_MB");
+        mb = s ? atol(s) : 48;
+        if (mb <= 0) mb = 48;
+    }
+    size_t per = (size_t)9 * P + (size_t)4 * Nb;
+    long sb = (long)((size_t)mb * 1024 * 1024 / per);
+    if (sb < 128) sb = 128;
+    if (sb > B) sb = B;
+    return (int)sb;
+}
+
+struct TrainPlan {
+    int HP, SB, ntiles, ntiles_blue, nsplit;
+    size_t off_small, off_hasblue, off_nll, off_part, off_spart, total;
+};
+static TrainPlan plan_train(int Nb, int Nr, int Nh, int B, int precision) {
+    TrainPlan p;
+    const int P = Nb + Nr;
+    const size_t ts = tsize(precision);
+    p.HP = pad_h(Nh);
+    p.SB = subbatch_size(P, Nb, B > 0 ? B : 1);
+    p.ntiles = (P + 127) / 128;
+    p.ntiles_blue = (Nb + 127) / 128;
+    int want = (4 * num_sms() + p.ntiles - 1) / p.ntiles;
+    if (want > p.SB) want = p.SB;
+    if (want < 1) want = 1;
+    p.nsplit = want;
+    size_t small_len = 2 * (size_t)p.HP + 2 * (size_t)p.HP * p.HP;
+    size_t o = 0;
+    p.off_small = o;   o = align_up(o + (size_t)p.SB * small_len * ts, 256);
+    p.off_hasblue = o; o = align_up(o + (size_t)(B > 0 ? B : 1) * 4, 256);
+    p.off_nll = o;     o = align_up(o + (size_t)(B > 0 ? B : 1) * ts, 256);
+    p.off_part = o;    o = align_up(o + (size_t)p.nsplit * part_len(P, Nb, Nh) * ts, 256);
+    p.off_spart = o;   o = align_up(o + (size_t)p.nsplit * p.ntiles * 3 * ts, 256);
+    p.total = o;
+    return p;
+}
+extern "C" size_t qfa_train_workspace_bytes(int Nb, int Nr, int Nh, int B, int precision) {
+    if (Nb < 0 || Nr < 0 || Nb + Nr <= 0 || Nh < 1 || Nh > 32 || B < 0) return 0;
+    return plan_train(Nb, Nr, Nh, B, precision).total;
+}
+extern "C" size_t qfa_predict_workspace_bytes(int, int, int, int, int) { return 256; }
+
+template <typename T>
+static Field<T> make_field(const QfaModel* m, const float* x, const float* err, const float* zabs,
+                           const uint8_t* mask) {
+    Field<T> f;
+    const int P = m->Nb + m->Nr;
+    f.x = x; f.err = err; f.zabs = zabs; f.mask = mask;
+    f.F = m->params;
+    f.Psi = m->params + (size_t)P * m->Nh;
+    f.omega = f.Psi + P;
+    f.scal = f.omega + m->Nb;
+    f.mu = m->mu;
+    f.Nb = m->Nb; f.P = P; f.Nh = m->Nh;
+    LawConst lc = law_constants(m->tau_law);
+    f.lt0 = (T)lc.t0; f.lbe = (T)lc.be; f.lC = (T)lc.C; f.llogzn = (T)log(lc.zn);
+    return f;
+}
+
+static int check_model(const QfaModel* m, int precision) {
+    if (!m || !m->params) return fail(QFA_ERR_NULL, "model / model->params is NULL");
+    if (m->Nb < 0 || m->Nr < 0 || m->Nb + m->Nr <= 0) return fail(QFA_ERR_SHAPE, "bad grid Nb=%d Nr=%d", m->Nb, m->Nr);
+    if (m->Nh < 1 || m->Nh > 32) return fail(QFA_ERR_NH, "Nh=%d unsupported (1..32)", m->Nh);
+    if (m->tau_law < 0 || m->tau_law > 3) return fail(QFA_ERR_LAW, "unknown tau law %d", m->tau_law);
+    if (precision != QFA_PREC_FP64 && precision != QFA_PREC_FP32 && precision != QFA_PREC_TF32)
+        return fail(QFA_ERR_PRECISION, "unknown precision mode %d", precision);
+    if (((uintptr_t)m->params & 15) != 0) return fail(QFA_ERR_ALIGN, "params must be 16-byte aligned");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------
+template <typename T, int HP, int MODE>
+static cudaError_t launch_gram(const GramArgs<T>& a, cudaStream_t st) {
+    using C = GramCfg<T, HP, MODE>;
+    auto kern = k_gram_solve<T, HP, MODE>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    int per_sm = (int)((size_t)220 * 1024 / (C::smem_bytes + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int grid = num_sms() * per_sm;
+    if (grid > a.B) grid = a.B;
+    if (grid < 1) return cudaSuccess;
+    kern<<<grid, C::NT, C::smem_bytes, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename T, int MODE>
+static cudaError_t dispatch_gram(int HP, const GramArgs<T>& a, cudaStream_t st) {
+    switch (HP) {
+        case 4: return launch_gram<T, 4, MODE>(a, st);
+        case 8: return launch_gram<T, 8, MODE>(a, st);
+        case 16: return launch_gram<T, 16, MODE>(a, st);
+        default: return launch_gram<T, 32, MODE>(a, st);
+    }
+}
+
+template <typename T>
+static cudaError_t dispatch_grad(int HP, const GradArgs<T>& a, int ntiles, cudaStream_t st) {
+    dim3 grid(ntiles, a.nsplit);
+    switch (HP) {
+        case 4: k_grad<T, 4><<<grid, 128, 0, st>>>(a); break;
+        case 8: k_grad<T, 8><<<grid, 128, 0, st>>>(a); break;
+        case 16: k_grad<T, 16><<<grid, 128, 0, st>>>(a); break;
+        default: k_grad<T, 32><<<grid, 128, 0, st>>>(a); break;
+    }
+    return cudaGetLastError();
+}
+
+template <typename T>
+static int train_accumulate_t(const QfaModel* m, const float* delta, const float* error, const float* zabs,
+                              const uint8_t* mask, int B, char* ws, const TrainPlan& pl, T* acc, T* nll_out,
+                              int flags, cudaStream_t st) {
+    const int P = m->Nb + m->Nr, Nb = m->Nb, Nh = m->Nh;
+    if (flags & QFA_FLAG_ZERO_ACC) CK(cudaMemsetAsync(acc, 0, qfa_acc_len(m->Nb, m->Nr, Nh) * sizeof(T), st));
+    if (B == 0) return 0;
+    T* small = reinterpret_cast<T*>(ws + pl.off_small);
+    float* hasblue = reinterpret_cast<float*>(ws + pl.off_hasblue);
+    T* nll = nll_out ? nll_out : reinterpret_cast<T*>(ws + pl.off_nll);
+    T* part = reinterpret_cast<T*>(ws + pl.off_part);
+    T* spart = reinterpret_cast<T*>(ws + pl.off_spart);
+    int nsplit_used = pl.nsplit;
+    for (int s0 = 0, it = 0; s0 < B; s0 += pl.SB, ++it) {
+        const int nb = (B - s0 < pl.SB) ? B - s0 : pl.SB;
+        Field<T> f = make_field<T>(m, delta + (size_t)s0 * P, error + (size_t)s0 * P,
+                                   zabs + (size_t)s0 * Nb, mask + (size_t)s0 * P);
+        GramArgs<T> ga;
+        ga.f = f; ga.B = nb; ga.small = small; ga.nll = nll + s0; ga.hasblue = hasblue + s0;
+        ga.hmean = nullptr; ga.hcov = nullptr; ga.cont = nullptr; ga.unc = nullptr;
+        CK((dispatch_gram<T, MODE_TRAIN>(pl.HP, ga, st)));
+        GradArgs<T> gr;
+        gr.f = f; gr.B = nb; gr.nsplit = nsplit_used; gr.small = small; gr.part = part; gr.spart = spart;
+        gr.accumulate = it > 0;
+        CK(dispatch_grad<T>(pl.HP, gr, pl.ntiles, st));
+    }
+    ReduceArgs<T> ra;
+    ra.part = part; ra.spart = spart; ra.nll = nll; ra.hasblue = hasblue; ra.scal = make_field<T>(m, 0, 0, 0, 0).scal;
+    ra.acc = acc; ra.P = P; ra.Nb = Nb; ra.Nh = Nh; ra.B = B; ra.nsplit = nsplit_used;
+    ra.ntiles_blue = pl.ntiles_blue; ra.ntiles = pl.ntiles;
+    size_t n_el = part_len(P, Nb, Nh);
+    int blocks = (int)((n_el + 255) / 256);
+    k_reduce<T><<<blocks, 256, 0, st>>>(ra);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qfa_train_accumulate(const QfaModel* model, const float* delta, const float* error,
+                                    const float* zabs, const uint8_t* mask, int B, void* workspace,
+                                    size_t workspace_bytes, void* acc, void* nll_per_spectrum, int precision,
+                                    int flags, void* stream) {
+    int rc = check_model(model, precision);
+    if (rc) return rc;
+    if (B < 0) return fail(QFA_ERR_SHAPE, "B=%d", B);
+    if (!acc) return fail(QFA_ERR_NULL, "acc is NULL");
+    if (B > 0 && (!delta || !error || !mask || (!zabs && model->Nb > 0)))
+        return fail(QFA_ERR_NULL, "delta/error/zabs/mask is NULL");
+    TrainPlan pl = plan_train(model->Nb, model->Nr, model->Nh, B, precision);
+    if (B > 0 && (!workspace || workspace_bytes < pl.total))
+        return fail(QFA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total, workspace_bytes);
+    if (((uintptr_t)workspace & 255) != 0) return fail(QFA_ERR_ALIGN, "workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == QFA_PREC_FP64)
+        return train_accumulate_t<double>(model, delta, error, zabs, mask, B, (char*)workspace, pl, (double*)acc,
+                                          (double*)nll_per_spectrum, flags, st);
+    // QFA_PREC_TF32 currently shares the float CUDA-core path
+    return train_accumulate_t<float>(model, delta, error, zabs, mask, B, (char*)workspace, pl, (float*)acc,
+                                     (float*)nll_per_spectrum, flags, st);
+}
+
+template <typename T>
+static int predict_t(const QfaModel* m, const float* flux, const float* error, const float* zabs,
+                     const uint8_t* mask, int B, T* nll, T* hmean, T* hcov, T* cont, T* unc, cudaStream_t st) {
+    GramArgs<T> ga;
+    ga.f = make_field<T>(m, flux, error, zabs, mask);
+    ga.B = B; ga.small = nullptr; ga.nll = nll; ga.hasblue = nullptr;
+    ga.hmean = hmean; ga.hcov = hcov; ga.cont = cont; ga.unc = unc;
+    CK((dispatch_gram<T, MODE_PREDICT>(pad_h(m->Nh), ga, st)));
+    return 0;
+}
+
+extern "C" int qfa_predict(const QfaModel* model, const float* flux, const float* error, const float* zabs,
+                           const uint8_t* mask, int B, void* workspace, size_t workspace_bytes, void* nll,
+                           void* hmean, void* hcov, void* cont, void* unc, int precision, int flags,
+                           void* stream) {
+    (void)workspace; (void)workspace_bytes; (void)flags;
+    int rc = check_model(model, precision);
+    if (rc) return rc;
+    if (B < 0) return fail(QFA_ERR_SHAPE, "B=%d", B);
+    if (!model->mu) return fail(QFA_ERR_NULL, "model->mu is NULL (prediction needs the mean spectrum)");
+    if (!nll) return fail(QFA_ERR_NULL, "nll is NULL");
+    if (B == 0) return 0;
+    if (!flux || !error || !mask || (!zabs && model->Nb > 0)) return fail(QFA_ERR_NULL, "flux/error/zabs/mask is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == QFA_PREC_FP64)
+        return predict_t<double>(model, flux, error, zabs, mask, B, (double*)nll, (double*)hmean, (double*)hcov,
+                                 (double*)cont, (double*)unc, st);
+    return predict_t<float>(model, flux, error, zabs, mask, B, (float*)nll, (float*)hmean, (float*)hcov,
+                            (float*)cont, (float*)unc, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// parameter-side kernels: finalize, Adam + clip, clip, smooth, batch preparation
+// ---------------------------------------------------------------------------------------
+struct PLayout {
+    size_t PH, P, Nb, n;          // n = param_len
+    size_t o_cnt, o_scnt, o_nll, o_nsp;
+};
+static PLayout playout(int Nb, int Nr, int Nh) {
+    PLayout L;
+    L.P = (size_t)Nb + Nr; L.Nb = Nb; L.PH = L.P * Nh; L.n = L.PH + L.P + L.Nb + 3;
+    L.o_cnt = L.n; L.o_scnt = L.o_cnt + L.P; L.o_nll = L.o_scnt + 3; L.o_nsp = L.o_nll + 1;
+    return L;
+}
+
+// gradient of packed element e from acc: sum / count (0/0 -> NaN, like model.py:104)
+template <typename T>
+__device__ __forceinline__ float grad_from_acc(const T* acc, const PLayout& L, size_t e, int Nh) {
+    T cnt;
+    if (e < L.PH) cnt = acc[L.o_cnt + e / Nh];
+    else if (e < L.PH + L.P) cnt = acc[L.o_cnt + (e - L.PH)];
+    else if (e < L.PH + L.P + L.Nb) cnt = acc[L.o_cnt + (e - L.PH - L.P)];
+    else cnt = acc[L.o_scnt + (e - L.PH - L.P - L.Nb)];
+    return (float)(acc[e] / cnt);
+}
+
+template <typename T>
+__global__ void k_finalize(const T* acc, PLayout L, int Nh, float* grads, float* loss) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < L.n) grads[e] = grad_from_acc(acc, L, e, Nh);
+    if (e == 0 && loss) loss[0] = (float)(acc[L.o_nll] / acc[L.o_nsp]);
+}
+
+__device__ __forceinline__ float clip_elem(float p, const PLayout& L, size_t e, float lo, float hi) {
+    if (e < L.PH) return p;                                                   // F: unbounded
+    if (e < L.PH + L.P + L.Nb) return fminf(fmaxf(p, lo), hi);                // Psi, omega (model.py:237-238)
+    size_t s = e - (L.PH + L.P + L.Nb);
+    if (s == 0) return fminf(fmaxf(p, 0.0f), 1.0f);                           // tau0 (model.py:239)
+    if (s == 1) return fminf(fmaxf(p, -5.0f), 5.0f);                          // c0   (model.py:241)
+    return fminf(fmaxf(p, 0.1f), 5.0f);                                       // beta (model.py:240)
+}
+
+template <typename T>
+__global__ void k_adam(float* p, float* m, float* v, const T* acc, const float* gin, PLayout L, int Nh,
+                       float lr, float b1, float b2, float eps, float wd, float bias1, float bias2,
+                       float lo, float hi) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= L.n) return;
+    float g = gin ? gin[e] : grad_from_acc(acc, L, e, Nh);
+    float pe = p[e];
+    g = g + wd * pe;                                  // optimizer.py:47
+    float me = (1.0f - b1) * g + b1 * m[e];           // optimizer.py:48
+    float ve = (1.0f - b2) * g * g + b2 * v[e];       // optimizer.py:49
+    m[e] = me; v[e] = ve;
+    float mh = me / bias1, vh = ve / bias2;           // optimizer.py:50-51
+    pe = pe - lr * mh / (sqrtf(vh) + eps);            // optimizer.py:52
+    p[e] = clip_elem(pe, L, e, lo, hi);               // model.py:316 -> 233-241
+}
+
+__global__ void k_clip(float* p, PLayout L, float lo, float hi) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < L.n) p[e] = clip_elem(p[e], L, e, lo, hi);
+}
+
+// box filter ignoring out-of-range taps; F columns: half-width 15, Psi/omega: half-width 7
+__global__ void k_smooth(const float* in, float* out, PLayout L, int Nh) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= L.n) return;
+    if (e < L.PH) {
+        long i = (long)(e / Nh); int k = (int)(e % Nh);
+        long lo = i - 15 < 0 ? 0 : i - 15, hi = i + 15 >= (long)L.P ? (long)L.P - 1 : i + 15;
+        float s = 0.f;
+        for (long j = lo; j <= hi; ++j) s += in[(size_t)j * Nh + k];
+        out[e] = s / (float)(hi - lo + 1);
+    } else if (e < L.PH + L.P + L.Nb) {
+        size_t base = (e < L.PH + L.P) ? L.PH : L.PH + L.P;
+        long n = (e < L.PH + L.P) ? (long)L.P : (long)L.Nb;
+        long i = (long)(e - base);
+        long lo = i - 7 < 0 ? 0 : i - 7, hi = i + 7 >= n ? n - 1 : i + 7;
+        float s = 0.f;
+        for (long j = lo; j <= hi; ++j) s += in[base + j];
+        out[e] = s / (float)(hi - lo + 1);
+    } else {
+        out[e] = in[e];
+    }
+}
+
+__global__ void k_prepare(const float* flux, const float* zq, const float* wav, const float* mu, size_t B, int Nb,
+                          int P, float lt0, float lbe, float lC, float lzn, float* zabs, float* delta) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= B * (size_t)P) return;
+    size_t b = gid / P; int i = (int)(gid % P);
+    float A = 1.0f;
+    if (i < Nb) {
+        float z = (1.0f + zq[b]) * wav[i] / 1215.67f - 1.0f;          // dataloader.py:102
+        if (zabs) zabs[b * (size_t)Nb + i] = z;
+        float tau = lt0 * powf((1.0f + z) / lzn, lbe) + lC;
+        A = expf(-tau);
+    }
+    if (delta) delta[gid] = flux[gid] - mu[i] * A;                    // dataloader.py:135-136
+}
+
+static int check_grid(int Nb, int Nr, int Nh) {
+    if (Nb < 0 || Nr < 0 || Nb + Nr <= 0) return fail(QFA_ERR_SHAPE, "bad grid Nb=%d Nr=%d", Nb, Nr);
+    if (Nh < 1 || Nh > 32) return fail(QFA_ERR_NH, "Nh=%d unsupported (1..32)", Nh);
+    return 0;
+}
+
+extern "C" int qfa_grads_finalize(const void* acc, int Nb, int Nr, int Nh, int precision, float* grads,
+                                  float* loss, void* stream) {
+    int rc = check_grid(Nb, Nr, Nh);
+    if (rc) return rc;
+    if (!acc || !grads) return fail(QFA_ERR_NULL, "acc/grads is NULL");
+    PLayout L = playout(Nb, Nr, Nh);
+    int blocks = (int)((L.n + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == QFA_PREC_FP64) k_finalize<double><<<blocks, 256, 0, st>>>((const double*)acc, L, Nh, grads, loss);
+    else k_finalize<float><<<blocks, 256, 0, st>>>((const float*)acc, L, Nh, grads, loss);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qfa_adam_clip_step(float* params, float* m, float* v, const void* acc, const float* grads_in,
+                                  int Nb, int Nr, int Nh, int precision, float lr, float b1, float b2, float eps,
+                                  float weight_decay, float bias1, float bias2, float min_value, float max_value,
+                                  void* stream) {
+    int rc = check_grid(Nb, Nr, Nh);
+    if (rc) return rc;
+    if (!params || !m || !v || (!acc && !grads_in)) return fail(QFA_ERR_NULL, "params/m/v/acc is NULL");
+    PLayout L = playout(Nb, Nr, Nh);
+    int blocks = (int)((L.n + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == QFA_PREC_FP64 && !grads_in)
+        k_adam<double><<<blocks, 256, 0, st>>>(params, m, v, (const double*)acc, grads_in, L, Nh, lr, b1, b2, eps,
+                                               weight_decay, bias1, bias2, min_value, max_value);
+    else
+        k_adam<float><<<blocks, 256, 0, st>>>(params, m, v, (const float*)acc, grads_in, L, Nh, lr, b1, b2, eps,
+                                              weight_decay, bias1, bias2, min_value, max_value);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qfa_clip(float* params, int Nb, int Nr, int Nh, float min_value, float max_value, void* stream) {
+    int rc = check_grid(Nb, Nr, Nh);
+    if (rc) return rc;
+    if (!params) return fail(QFA_ERR_NULL, "params is NULL");
+    PLayout L = playout(Nb, Nr, Nh);
+    k_clip<<<(int)((L.n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, L, min_value, max_value);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qfa_smooth(const float* params_in, float* params_out, int Nb, int Nr, int Nh, void* stream) {
+    int rc = check_grid(Nb, Nr, Nh);
+    if (rc) return rc;
+    if (!params_in || !params_out) return fail(QFA_ERR_NULL, "params is NULL");
+    if (params_in == params_out) return fail(QFA_ERR_UNSUPPORTED, "qfa_smooth cannot run in place");
+    PLayout L = playout(Nb, Nr, Nh);
+    k_smooth<<<(int)((L.n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params_in, params_out, L, Nh);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qfa_prepare_batch(const float* flux, const float* zqso, const float* wav, const float* mu, int B,
+                                 int Nb, int Nr, int tau_law, float* zabs_out, float* delta_out, void* stream) {
+    if (Nb < 0 || Nr < 0 || Nb + Nr <= 0 || B < 0) return fail(QFA_ERR_SHAPE, "bad shape");
+    if (tau_law < 0 || tau_law > 3) return fail(QFA_ERR_LAW, "unknown tau law %d", tau_law);
+    if (!zqso || !wav || (delta_out && (!flux || !mu))) return fail(QFA_ERR_NULL, "NULL input");
+    if (B == 0) return 0;
+    LawConst lc = law_constants(tau_law);
+    size_t n = (size_t)B * (Nb + Nr);
+    k_prepare<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        flux, zqso, wav, mu, (size_t)B, Nb, Nb + Nr, (float)lc.t0, (float)lc.be, (float)lc.C, (float)lc.zn, zabs_out,
+        delta_out);
+    CK(cudaGetLastError());
+    return 0;
+}
