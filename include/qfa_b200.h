@@ -163,6 +163,15 @@ int qfa_prepare_batch(const float* flux, const float* zqso, const float* wav, co
                       int B, int Nb, int Nr, int tau_law,
                       float* zabs_out, float* delta_out, void* stream);
 
+/*
+ * Hardware self-test of the tcgen05 / TMEM / bulk-copy plumbing used by the QFA_PREC_TF32 kernels:
+ * D[128][64] = [ A[128][32] * B[48][32]^T | A * B[32:48]^T ] with B given as the swizzled
+ * shared-memory image (hi and lo parts).  split != 0 selects the 3xTF32 product.
+ * err_flag (device int) is set to 1 if an mbarrier wait timed out.  Test-only entry point.
+ */
+int qfa_selftest_umma(const float* A, const float* Bimg_hi, const float* Bimg_lo, float* D, int split,
+                      int* err_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,7 @@ SIGNATURES = {
     "qfa_clip": (_I, [_VP, _I, _I, _I, _F, _F, _VP]),
     "qfa_smooth": (_I, [_VP, _VP, _I, _I, _I, _VP]),
     "qfa_prepare_batch": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP]),
+    "qfa_selftest_umma": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP]),
 }
 
 

@@ -8,6 +8,7 @@
 
 #include "../../include/qfa_b200.h"
 #include "qfa_kernels.cuh"
+#include "qfa_tc_selftest.cuh"
 
 using namespace qfa;
 
@@ -263,8 +264,8 @@ extern "C" int qfa_predict(const QfaModel* model, const float* flux, const float
     if (rc) return rc;
     if (B < 0) return fail(QFA_ERR_SHAPE, "B=%d", B);
     if (!model->mu) return fail(QFA_ERR_NULL, "model->mu is NULL (prediction needs the mean spectrum)");
-    if (!nll) return fail(QFA_ERR_NULL, "nll is NULL");
     if (B == 0) return 0;
+    if (!nll) return fail(QFA_ERR_NULL, "nll is NULL");
     if (!flux || !error || !mask || (!zabs && model->Nb > 0)) return fail(QFA_ERR_NULL, "flux/error/zabs/mask is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == QFA_PREC_FP64)
@@ -447,6 +448,19 @@ extern "C" int qfa_prepare_batch(const float* flux, const float* zqso, const flo
     k_prepare<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         flux, zqso, wav, mu, (size_t)B, Nb, Nb + Nr, (float)lc.t0, (float)lc.be, (float)lc.C, (float)lc.zn, zabs_out,
         delta_out);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// tcgen05 self-test (see qfa_tc_selftest.cuh)
+// ---------------------------------------------------------------------------------------
+extern "C" int qfa_selftest_umma(const float* A, const float* Bimg_hi, const float* Bimg_lo, float* D, int split,
+                                 int* err_flag, void* stream) {
+    if (!A || !Bimg_hi || !Bimg_lo || !D || !err_flag) return fail(QFA_ERR_NULL, "NULL argument");
+    const int smem = 49152 + 1024;
+    CK(cudaFuncSetAttribute(k_selftest_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_selftest_umma<<<1, 128, smem, (cudaStream_t)stream>>>(A, Bimg_hi, Bimg_lo, D, split, err_flag);
     CK(cudaGetLastError());
     return 0;
 }

@@ -279,6 +279,105 @@ class QFA(object):
                                  _ptr(out.get("cont")), _ptr(out.get("unc")), self._prec, 0, self._stream()),
                    "qfa_predict")
 
+    # ------------------------------------------------------------------ host-buffer (end-to-end) paths
+    def _host_pipeline(self, arrays, chunk, body):
+        """Streams `arrays` (CPU tensors, ideally pinned) through the GPU in chunks of `chunk`
+        spectra: H2D on a copy stream, `body(dev_inputs, lo, hi, slot)` on the current stream,
+        double-buffered so that copies overlap compute.  Returns the list of per-slot events the
+        caller may wait on."""
+        dev = self.device
+        B = arrays[0].shape[0]
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_h2d"):
+            self._h2d = torch.cuda.Stream(dev)
+            self._d2h = torch.cuda.Stream(dev)
+        key = (chunk,) + tuple((a.shape[1:], a.dtype) for a in arrays)
+        if getattr(self, "_stage_key", None) != key:
+            self._stage = [[torch.empty((chunk,) + tuple(a.shape[1:]), dtype=a.dtype, device=dev) for a in arrays]
+                           for _ in range(2)]
+            self._stage_key = key
+        free = [None, None]          # compute finished reading slot
+        for ci, lo in enumerate(range(0, B, chunk)):
+            hi = min(lo + chunk, B)
+            slot = ci & 1
+            with torch.cuda.stream(self._h2d):
+                if free[slot] is not None:
+                    self._h2d.wait_event(free[slot])
+                ins = []
+                for a, st in zip(arrays, self._stage[slot]):
+                    st[:hi - lo].copy_(a[lo:hi], non_blocking=True)
+                    ins.append(st[:hi - lo])
+                ready = torch.cuda.Event()
+                ready.record(self._h2d)
+            cur.wait_event(ready)
+            body(ins, lo, hi, slot)
+            free[slot] = torch.cuda.Event()
+            free[slot].record(cur)
+
+    def forward_host(self, delta, error, zabs, mask, chunk=8192):
+        """QFA.forward for HOST tensors: inputs are streamed H2D in chunks (overlapped with the
+        kernels), the packed gradient and the loss are copied back D2H.  Returns CPU tensors."""
+        self._require_cuda()
+        mask = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+        first = [True]
+
+        def body(ins, lo, hi, slot):
+            self.accumulate(ins[0], ins[1], ins[2], ins[3], zero=first[0])
+            first[0] = False
+        if delta.shape[0] == 0:
+            self.accumulate(delta.to(self.device), error.to(self.device), zabs.to(self.device), mask.to(self.device))
+        else:
+            self._host_pipeline([delta, error, zabs, mask], chunk, body)
+        self._allreduce(self._acc)
+        loss, grads = self.finalize(self._acc)
+        if not hasattr(self, "_host_grads"):
+            self._host_grads = torch.empty(self.Nparams + 1, dtype=torch.float32).pin_memory()
+        self._host_grads[:self.Nparams].copy_(grads.packed, non_blocking=True)
+        self._host_grads[self.Nparams:].copy_(loss.view(1), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._host_grads[self.Nparams:].view(1, 1), self._as_dict(self._host_grads[:self.Nparams])
+
+    def predict_host(self, flux, error, zabs, mask, out=None, want=("nll", "hmean", "hcov", "cont", "unc"),
+                     chunk=8192):
+        """predict_batch for HOST tensors (reference main.py:94-98 moves every spectrum H2D and every
+        result D2H): chunked, double-buffered H2D -> kernel -> D2H pipeline on three streams.
+        `out`: optional dict of (pinned) CPU tensors to fill."""
+        self._require_cuda()
+        B = flux.shape[0]
+        dt = self._tdtype
+        shapes = {"nll": (B,), "hmean": (B, self.Nh), "hcov": (B, self.Nh, self.Nh), "cont": (B, self.Npix),
+                  "unc": (B, self.Npix)}
+        names = ["nll"] + [k for k in ("hmean", "hcov", "cont", "unc") if k in want]
+        if out is None:
+            out = {k: torch.empty(shapes[k], dtype=dt).pin_memory() for k in names}
+        mask = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+        okey = (chunk, dt, tuple(names))
+        if getattr(self, "_ostage_key", None) != okey:
+            self._ostage = [{k: torch.empty((chunk,) + shapes[k][1:], dtype=dt, device=self.device) for k in names}
+                            for _ in range(2)]
+            self._ostage_key = okey
+        drained = [None, None]
+        cur = torch.cuda.current_stream(self.device)
+
+        def body(ins, lo, hi, slot):
+            n = hi - lo
+            if drained[slot] is not None:
+                cur.wait_event(drained[slot])
+            o = {k: v[:n] for k, v in self._ostage[slot].items()}
+            self.predict_into(ins[0], ins[1], ins[2], ins[3], o)
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(self._d2h):
+                self._d2h.wait_event(done)
+                for k in names:
+                    out[k][lo:hi].copy_(o[k], non_blocking=True)
+                drained[slot] = torch.cuda.Event()
+                drained[slot].record(self._d2h)
+        if B > 0:
+            self._host_pipeline([flux, error, zabs, mask], chunk, body)
+            self._d2h.synchronize()
+        return out
+
     def nll_batch(self, flux, error, zabs, mask):
         """Per-spectrum NEGATIVE log-likelihood only (likelihood / out-of-distribution scoring)."""
         return self.predict_batch(flux, error, zabs, mask, want=("nll",))["nll"]

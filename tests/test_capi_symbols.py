@@ -1,0 +1,48 @@
+"""CPU: libqfa_b200.so builds for sm_100a, loads, and exports every symbol include/qfa_b200.h declares.
+No compute call is made (there is no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+from qfa_b200 import _lib
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "qfa_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qfa_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_bound_and_exported():
+    _lib.build()
+    names = declared_symbols()
+    assert len(names) >= 12
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), n
+
+
+def test_host_side_entry_points_without_gpu():
+    L = _lib.lib()
+    assert L.qfa_abi_version() == 1
+    assert L.qfa_param_len(720, 1193, 8) == 1913 * 8 + 1913 + 720 + 3          # reference model.py:42
+    assert L.qfa_acc_len(720, 1193, 8) == 1913 * 8 + 1913 + 720 + 3 + 1913 + 3 + 2 + 1913
+    assert L.qfa_train_workspace_bytes(720, 1193, 8, 500, 1) > 0
+    # argument errors are reported on the host, before any launch, with a message
+    rc = L.qfa_clip(None, 720, 1193, 8, 1e-3, 2.0, None)
+    assert rc == -1 and b"NULL" in L.qfa_last_error_string()
+    rc = L.qfa_clip(ctypes.c_void_p(16), 720, 1193, 64, 1e-3, 2.0, None)
+    assert rc == -3
+    with pytest.raises(_lib.QfaError):
+        _lib.check(rc, "qfa_clip")
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert not re.search(r"sm_(?!100a)\d+", out)

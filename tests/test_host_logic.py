@@ -1,0 +1,139 @@
+"""CPU: host-side mirror of the reference API (state container, npz layout, tau-law resolution,
+optimizer bookkeeping).  The likelihood/gradient/prediction path must refuse to run without CUDA."""
+import os
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD, load_case, relerr
+from qfa_b200 import QFA, Adam, step_scheduler, QfaError
+from qfa_b200 import utils as U
+from qfa_b200 import synth
+
+cpu = torch.device("cpu")
+
+
+def test_constructor_matches_reference_defaults():
+    m = QFA(720, 1193, 8, cpu)
+    assert (m.Npix, m.Nparams) == (1913, 1913 * 8 + 1913 + 720 + 3)            # model.py:41-42
+    assert m.F.shape == (1913, 8) and m.Psi.shape == (1913,) and m.omega.shape == (720,)
+    assert m.tau0.shape == () and float(m.tau0) == pytest.approx(0.02)         # quirk Q9: code, not docstring
+    assert float(m.c0) == pytest.approx(0.3) and float(m.beta) == pytest.approx(2.0)
+    assert float(m.F.min()) >= -0.5 and float(m.F.max()) <= 0.5
+    assert set(m.parameters) == {"F", "Psi", "omega", "tau0", "c0", "beta"}
+    assert m.mu is None and m.min_value == 1e-3 and m.max_value == 2.
+
+
+def test_parameters_setter_clips_like_reference():
+    m = QFA(5, 7, 2, cpu)
+    p = {k: v.clone() for k, v in m.parameters.items()}
+    p["Psi"][:] = 5.0; p["omega"][:] = -1.0
+    p["tau0"] = torch.tensor(3.0); p["beta"] = torch.tensor(0.0); p["c0"] = torch.tensor(-9.0)
+    m.parameters = p                                                            # model.py:308-316
+    assert float(m.Psi.max()) == 2.0 and float(m.omega.min()) == pytest.approx(1e-3)
+    assert float(m.tau0) == 1.0 and float(m.beta) == pytest.approx(0.1) and float(m.c0) == -5.0
+
+
+def test_npz_roundtrip_and_c0_quirk(tmp_path):
+    k = np.load(os.path.join(GOLD, "kat_sdss.npz"))
+    path = tmp_path / "params.npz"
+    np.savez(path, **{key[6:]: k[key] for key in k.files if key.startswith("param_")})
+    m = QFA(720, 1193, 8, cpu)
+    m.load_from_npz(str(path))
+    assert m.F.dtype == torch.float32                                           # file's F is float64
+    assert float(m.c0) == float(m.beta) == pytest.approx(float(k["param_beta"]))   # quirk Q1 (model.py:295)
+    m2 = QFA(720, 1193, 8, cpu)
+    m2.load_from_npz(str(path), reference_c0_bug=False)
+    assert float(m2.c0) == pytest.approx(float(k["param_c0"]))
+    m.save_to_npz(str(tmp_path), "out.npz")
+    o = np.load(tmp_path / "out.npz")
+    assert sorted(o.files) == sorted(["mu", "F", "Psi", "omega", "tau0", "c0", "beta"])   # model.py:280
+    assert all(o[f].dtype == np.float32 for f in o.files) and o["tau0"].shape == ()
+    assert np.array_equal(o["F"], k["param_F"].astype(np.float32))
+
+
+def test_tau_law_resolution():
+    assert U.resolve_tau_law(U.default_tau) == 0
+    assert U.resolve_tau_law(partial(U.tau, which="kamble")) == 2
+    assert U.resolve_tau_law("mock") == 3
+    with pytest.raises(QfaError):
+        U.resolve_tau_law(lambda z: z)
+    with pytest.raises(QfaError):
+        U.resolve_tau_law(partial(U.tau, which="nope"))
+    z = torch.tensor([2.0, 3.0])
+    assert torch.allclose(U.tau(z, "becker"), 0.751 * ((1 + z) / 4.5) ** 2.9 - 0.132)
+    wav, Nb, Nr = U.wavelength_grid()
+    assert (len(wav), Nb, Nr) == (1913, 720, 1193)                              # dataloader.py:61-63
+    for g, shape in (("sdss", (1913, 720)), ("l32", (1000, 377)), ("desi", (9243, 2238))):
+        assert (synth.GRIDS[g].Npix, synth.GRIDS[g].Nb) == shape
+
+
+def test_no_cpu_fallback_for_hot_path():
+    c = load_case("tiny5")
+    m = QFA(c["Nb"], c["F"].shape[0] - c["Nb"], 5, cpu, model_params=c)
+    m.mu = c["mu"]
+    T = torch.tensor
+    with pytest.raises(QfaError):
+        m.forward(T(c["delta"]), T(c["error"]), T(c["zabs"]), T(c["mask"]))
+    with pytest.raises(QfaError):
+        m.prediction_for_single_spectra(T(c["flux"][0]), T(c["error"][0]), T(c["zabs"][0]), T(c["mask"][0]))
+    with pytest.raises(QfaError):
+        QFA(10, 10, 33, cpu)
+
+
+def test_adam_dict_path_and_scheduler_match_reference_golden():
+    """optimizer.py:47-52,98 through the torch-op path (dicts of ordinary tensors)."""
+    g = dict(np.load(os.path.join(GOLD, "train_tiny_f32.npz")))
+    c = load_case("train")
+    keys = ("F", "Psi", "omega", "tau0", "c0", "beta")
+    sch = step_scheduler(0.9, 2)
+    assert sch(0, 1.0) == 1.0 and sch(1, 1.0) == 0.9 and sch(3, 1.0) == pytest.approx(0.81)
+    from oracle import qfa_dense
+    P = {k: torch.tensor(c[k]) for k in keys}
+    P["Psi"] = torch.ones_like(P["Psi"]); P["omega"] = torch.ones_like(P["omega"])
+    T = torch.tensor
+    _, grads = qfa_dense.forward(P, T(c["delta"][:6]), T(c["error"][:6]), T(c["zabs"][:6]), T(c["mask"][:6]),
+                                 c["Nb"], c["law"])
+    opt = Adam(params=P, device=cpu, scheduler=sch, learning_rate=1e-2, weight_decay=0.1)
+    m = QFA(c["Nb"], c["F"].shape[0] - c["Nb"], 4, cpu)
+    m.parameters = opt.update(P, grads)
+    for k in keys:
+        assert relerr(m.parameters[k].numpy(), g["step_" + k]) < 1e-5, k
+    opt.step()
+    assert opt.i == 1 and opt.scheduled_lr == pytest.approx(1e-2 * 0.9)
+    opt.reset(P)
+    assert opt.i == 0 and float(opt.m["F"].abs().max()) == 0.0
+
+
+def test_smooth_host_matches_reference_golden():
+    g = dict(np.load(os.path.join(GOLD, "train_tiny_f32.npz")))
+    c = load_case("train")
+    m = QFA(c["Nb"], c["F"].shape[0] - c["Nb"], 4, cpu, model_params=c)
+    m.smooth()
+    for k in ("F", "Psi", "omega"):
+        assert relerr(m.parameters[k].numpy(), g["smooth_" + k]) < 1e-6
+
+
+def test_synthetic_loader_protocol_and_sharding():
+    grid = synth.GridSpec("t", 1150.0, 6e-4, 96)
+    P, mu = synth.smooth_random_params(grid, 4, seed=1)
+    data = synth.make_spectra(P, mu, grid, 40, seed=2)
+    assert data["mask"].dtype == torch.bool and data["zabs"].shape == (40, grid.Nb)
+    assert bool((data["flux"][~data["mask"]] == -999).all())
+    seen = []
+    for rank in range(2):
+        ld = synth.SyntheticLoader(data, mu, batch_size=8, rank=rank, world=2, seed=5)
+        assert ld.data_size == 40 and ld.batch_size == 8 and len(ld.mu) == 96
+        ld.rewind()
+        n = 0
+        while ld.have_next_batch():
+            d, e, z, m = ld.next_batch()
+            assert d.shape[0] <= 4 and z.shape[1] == grid.Nb
+            n += d.shape[0]
+            seen.append(d)
+        assert n == 20
+    allrows = torch.cat(seen)
+    assert allrows.shape[0] == 40
+    assert torch.equal(torch.sort(allrows[:, 0])[0], torch.sort(data["delta"][:, 0])[0])
