@@ -9,6 +9,7 @@
 #include "../../include/qfa_b200.h"
 #include "qfa_kernels.cuh"
 #include "qfa_tc_selftest.cuh"
+#include "qfa_tc_gram.cuh"
 
 using namespace qfa;
 
@@ -109,7 +110,30 @@ extern "C" size_t qfa_train_workspace_bytes(int Nb, int Nr, int Nh, int B, int p
     if (Nb < 0 || Nr < 0 || Nb + Nr <= 0 || Nh < 1 || Nh > 32 || B < 0) return 0;
     return plan_train(Nb, Nr, Nh, B, precision).total;
 }
-extern "C" size_t qfa_predict_workspace_bytes(int, int, int, int, int) { return 256; }
+
+// ---- tensor-core path (QFA_PREC_TF32, Nh <= 8): static operand images live in the workspace
+struct TcPlan {
+    int nkb, npt, ntiles;
+    size_t off_pb, off_qa, total;
+};
+static inline bool tc_eligible(int Nh, int precision) { return precision == QFA_PREC_TF32 && Nh <= tcg::HP; }
+static TcPlan plan_tc(int Nb, int Nr, int B, bool want_qa) {
+    TcPlan p;
+    const int P = Nb + Nr;
+    p.nkb = (P + tcg::KB - 1) / tcg::KB;
+    p.npt = (P + tcg::PT - 1) / tcg::PT;
+    p.ntiles = (B + tcg::TS - 1) / tcg::TS;
+    size_t o = 0;
+    p.off_pb = o; o = align_up(o + (size_t)p.nkb * tcg::PB_TILE, 1024);
+    p.off_qa = o; if (want_qa) o = align_up(o + (size_t)p.npt * tcg::QA_TILE, 1024);
+    p.total = o + 256;
+    return p;
+}
+extern "C" size_t qfa_predict_workspace_bytes(int Nb, int Nr, int Nh, int B, int precision) {
+    if (Nb < 0 || Nr < 0 || Nb + Nr <= 0 || Nh < 1 || Nh > 32 || B < 0) return 0;
+    if (tc_eligible(Nh, precision)) return plan_tc(Nb, Nr, B, true).total;
+    return 256;
+}
 
 template <typename T>
 static Field<T> make_field(const QfaModel* m, const float* x, const float* err, const float* zabs,
@@ -255,6 +279,35 @@ static int predict_t(const QfaModel* m, const float* flux, const float* error, c
     return 0;
 }
 
+static int predict_tc(const QfaModel* m, const float* flux, const float* error, const float* zabs, const uint8_t* mask,
+                      int B, char* ws, const TcPlan& pl, float* nll, float* hmean, float* hcov, float* cont, float* unc,
+                      bool want_o, cudaStream_t st) {
+    using namespace tcg;
+    using C = Cfg<TC_PREDICT>;
+    float* PB = reinterpret_cast<float*>(ws + pl.off_pb);
+    float* QA = reinterpret_cast<float*>(ws + pl.off_qa);
+    const int P = m->Nb + m->Nr;
+    const size_t n_el = (size_t)pl.nkb * PB_ROWS * KB + (want_o ? (size_t)pl.npt * 2 * PT * KB : 0);
+    int blocks = (int)((n_el + 255) / 256);
+    if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+    k_tc_build_images<<<blocks, 256, 0, st>>>(m->params, P, m->Nh, PB, pl.nkb, want_o ? QA : nullptr, want_o ? pl.npt : 0);
+    CK(cudaGetLastError());
+    static bool attr_done = false;
+    if (!attr_done) {
+        CK(cudaFuncSetAttribute(k_tc_gram<TC_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_done = true;
+    }
+    TcGramArgs a;
+    a.f = make_field<float>(m, flux, error, zabs, mask);
+    a.B = B; a.ntiles = pl.ntiles; a.nkb = pl.nkb; a.npt = pl.npt;
+    a.PB = PB; a.QA = QA; a.nll = nll; a.hmean = hmean; a.hcov = hcov; a.cont = cont; a.unc = unc;
+    a.sm_b2 = nullptr; a.sm_kc = nullptr; a.hasblue = nullptr;
+    int grid = pl.ntiles < num_sms() ? pl.ntiles : num_sms();
+    k_tc_gram<TC_PREDICT><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(a);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int qfa_predict(const QfaModel* model, const float* flux, const float* error, const float* zabs,
                            const uint8_t* mask, int B, void* workspace, size_t workspace_bytes, void* nll,
                            void* hmean, void* hcov, void* cont, void* unc, int precision, int flags,
@@ -268,6 +321,15 @@ extern "C" int qfa_predict(const QfaModel* model, const float* flux, const float
     if (!nll) return fail(QFA_ERR_NULL, "nll is NULL");
     if (!flux || !error || !mask || (!zabs && model->Nb > 0)) return fail(QFA_ERR_NULL, "flux/error/zabs/mask is NULL");
     cudaStream_t st = (cudaStream_t)stream;
+    if (tc_eligible(model->Nh, precision)) {
+        const bool want_o = cont || unc;
+        TcPlan pl = plan_tc(model->Nb, model->Nr, B, true);
+        if (!workspace || workspace_bytes < pl.total)
+            return fail(QFA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total, workspace_bytes);
+        if (((uintptr_t)workspace & 255) != 0) return fail(QFA_ERR_ALIGN, "workspace must be 256-byte aligned");
+        return predict_tc(model, flux, error, zabs, mask, B, (char*)workspace, pl, (float*)nll, (float*)hmean,
+                          (float*)hcov, (float*)cont, (float*)unc, want_o, st);
+    }
     if (precision == QFA_PREC_FP64)
         return predict_t<double>(model, flux, error, zabs, mask, B, (double*)nll, (double*)hmean, (double*)hcov,
                                  (double*)cont, (double*)unc, st);

@@ -273,7 +273,7 @@ class QFA(object):
         L = _lib.lib()
         B = flux.shape[0]
         st = self._struct(need_mu=True)
-        ws = self._workspace(256)
+        ws = self._workspace(L.qfa_predict_workspace_bytes(self.Nb, self.Nr, self.Nh, B, self._prec))
         _lib.check(L.qfa_predict(ctypes.byref(st), _ptr(flux), _ptr(error), _ptr(zabs), _ptr(mask), B, _ptr(ws),
                                  ws.numel(), _ptr(out["nll"]), _ptr(out.get("hmean")), _ptr(out.get("hcov")),
                                  _ptr(out.get("cont")), _ptr(out.get("unc")), self._prec, 0, self._stream()),
