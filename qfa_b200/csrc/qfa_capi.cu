@@ -10,6 +10,7 @@
 #include "qfa_kernels.cuh"
 #include "qfa_tc_selftest.cuh"
 #include "qfa_tc_gram.cuh"
+#include "qfa_tc_grad.cuh"
 
 using namespace qfa;
 
@@ -106,17 +107,26 @@ static TrainPlan plan_train(int Nb, int Nr, int Nh, int B, int precision) {
     p.total = o;
     return p;
 }
-extern "C" size_t qfa_train_workspace_bytes(int Nb, int Nr, int Nh, int B, int precision) {
-    if (Nb < 0 || Nr < 0 || Nb + Nr <= 0 || Nh < 1 || Nh > 32 || B < 0) return 0;
-    return plan_train(Nb, Nr, Nh, B, precision).total;
-}
-
 // ---- tensor-core path (QFA_PREC_TF32, Nh <= 8): static operand images live in the workspace
 struct TcPlan {
     int nkb, npt, ntiles;
     size_t off_pb, off_qa, total;
 };
 static inline bool tc_eligible(int Nh, int precision) { return precision == QFA_PREC_TF32 && Nh <= tcg::HP; }
+// The tensor-core kernels work on tiles of 128 spectra; below this batch size the float CUDA-core kernels
+// (one CTA per spectrum) fill the GPU better.  QFA_FLAG_FORCE_TENSOR overrides (tests, small-batch profiling).
+static int tc_min_batch() {
+    static int v = -1;
+    if (v < 0) {
+        const char* s = getenv("QFA_TC_MIN_BATCH");
+        v = s ? atoi(s) : 1024;
+        if (v < 0) v = 0;
+    }
+    return v;
+}
+static inline bool tc_use(int Nh, int precision, int B, int flags) {
+    return tc_eligible(Nh, precision) && (B >= tc_min_batch() || (flags & QFA_FLAG_FORCE_TENSOR));
+}
 static TcPlan plan_tc(int Nb, int Nr, int B, bool want_qa) {
     TcPlan p;
     const int P = Nb + Nr;
@@ -129,6 +139,43 @@ static TcPlan plan_tc(int Nb, int Nr, int B, bool want_qa) {
     p.total = o + 256;
     return p;
 }
+struct TcTrainPlan {
+    TcPlan t;
+    int nchunks, nsplit, ntiles_blue;
+    size_t off_b2, off_kc, off_hasblue, off_nll, off_part, off_spart, total;
+};
+static TcTrainPlan plan_tc_train(int Nb, int Nr, int Nh, int B) {
+    TcTrainPlan p;
+    const int P = Nb + Nr;
+    p.t = plan_tc(Nb, Nr, B, true);
+    p.nchunks = (B + tcg::GC - 1) / tcg::GC;
+    int ns = num_sms() / p.t.npt;
+    if (ns > p.nchunks) ns = p.nchunks;
+    if (ns < 1) ns = 1;
+    p.nsplit = ns;
+    p.ntiles_blue = (Nb + tcg::PT - 1) / tcg::PT;
+    size_t o = p.t.total;
+    o = align_up(o, 1024);
+    p.off_b2 = o;      o = align_up(o + (size_t)p.t.ntiles * tcg::B2_TILE, 1024);
+    p.off_kc = o;      o = align_up(o + (size_t)p.t.ntiles * 4 * tcg::KC_TILE, 1024);
+    p.off_hasblue = o; o = align_up(o + (size_t)(B > 0 ? B : 1) * 4, 256);
+    p.off_nll = o;     o = align_up(o + (size_t)(B > 0 ? B : 1) * 4, 256);
+    p.off_part = o;    o = align_up(o + (size_t)p.nsplit * part_len(P, Nb, Nh) * 4, 256);
+    p.off_spart = o;   o = align_up(o + (size_t)p.nsplit * p.t.npt * 3 * 4, 256);
+    p.total = o;
+    return p;
+}
+
+extern "C" size_t qfa_train_workspace_bytes(int Nb, int Nr, int Nh, int B, int precision) {
+    if (Nb < 0 || Nr < 0 || Nb + Nr <= 0 || Nh < 1 || Nh > 32 || B < 0) return 0;
+    size_t cc = plan_train(Nb, Nr, Nh, B, precision).total;
+    if (tc_eligible(Nh, precision)) {
+        size_t tc = plan_tc_train(Nb, Nr, Nh, B).total;
+        return tc > cc ? tc : cc;
+    }
+    return cc;
+}
+
 extern "C" size_t qfa_predict_workspace_bytes(int Nb, int Nr, int Nh, int B, int precision) {
     if (Nb < 0 || Nr < 0 || Nb + Nr <= 0 || Nh < 1 || Nh > 32 || B < 0) return 0;
     if (tc_eligible(Nh, precision)) return plan_tc(Nb, Nr, B, true).total;
@@ -245,6 +292,56 @@ static int train_accumulate_t(const QfaModel* m, const float* delta, const float
     return 0;
 }
 
+static int train_accumulate_tc(const QfaModel* m, const float* delta, const float* error, const float* zabs,
+                               const uint8_t* mask, int B, char* ws, const TcTrainPlan& pl, float* acc, float* nll_out,
+                               int flags, cudaStream_t st) {
+    using namespace tcg;
+    const int P = m->Nb + m->Nr, Nb = m->Nb, Nh = m->Nh;
+    if (flags & QFA_FLAG_ZERO_ACC) CK(cudaMemsetAsync(acc, 0, qfa_acc_len(m->Nb, m->Nr, Nh) * sizeof(float), st));
+    if (B == 0) return 0;
+    float* PB = reinterpret_cast<float*>(ws + pl.t.off_pb);
+    float* QA = reinterpret_cast<float*>(ws + pl.t.off_qa);
+    float* sm_b2 = reinterpret_cast<float*>(ws + pl.off_b2);
+    float* sm_kc = reinterpret_cast<float*>(ws + pl.off_kc);
+    float* hasblue = reinterpret_cast<float*>(ws + pl.off_hasblue);
+    float* nll = nll_out ? nll_out : reinterpret_cast<float*>(ws + pl.off_nll);
+    float* part = reinterpret_cast<float*>(ws + pl.off_part);
+    float* spart = reinterpret_cast<float*>(ws + pl.off_spart);
+    const size_t n_el = (size_t)pl.t.nkb * PB_ROWS * KB + (size_t)pl.t.npt * 2 * PT * KB;
+    int blocks = (int)((n_el + 255) / 256);
+    if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+    k_tc_build_images<<<blocks, 256, 0, st>>>(m->params, P, Nh, PB, pl.t.nkb, QA, pl.t.npt);
+    CK(cudaGetLastError());
+    static bool attr_done = false;
+    if (!attr_done) {
+        CK(cudaFuncSetAttribute(k_tc_gram<TC_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<TC_TRAIN>::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_tc_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, GradSmem::BYTES));
+        attr_done = true;
+    }
+    Field<float> f = make_field<float>(m, delta, error, zabs, mask);
+    TcGramArgs a;
+    a.f = f; a.B = B; a.ntiles = pl.t.ntiles; a.nkb = pl.t.nkb; a.npt = pl.t.npt;
+    a.PB = PB; a.QA = QA; a.nll = nll; a.hmean = nullptr; a.hcov = nullptr; a.cont = nullptr; a.unc = nullptr;
+    a.sm_b2 = sm_b2; a.sm_kc = sm_kc; a.hasblue = hasblue;
+    int grid = pl.t.ntiles < num_sms() ? pl.t.ntiles : num_sms();
+    k_tc_gram<TC_TRAIN><<<grid, NTHREADS, Cfg<TC_TRAIN>::SMEM_BYTES, st>>>(a);
+    CK(cudaGetLastError());
+    TcGradArgs ga;
+    ga.f = f; ga.B = B; ga.nchunks = pl.nchunks; ga.nsplit = pl.nsplit; ga.QA = QA; ga.sm_b2 = sm_b2; ga.sm_kc = sm_kc;
+    ga.zero = reinterpret_cast<const uint8_t*>(PB) + sw128_offset_host(36, 0);
+    ga.part = part; ga.spart = spart; ga.accumulate = 0;
+    k_tc_grad<<<dim3(pl.t.npt, pl.nsplit), NTHREADS, GradSmem::BYTES, st>>>(ga);
+    CK(cudaGetLastError());
+    ReduceArgs<float> ra;
+    ra.part = part; ra.spart = spart; ra.nll = nll; ra.hasblue = hasblue; ra.scal = f.scal;
+    ra.acc = acc; ra.P = P; ra.Nb = Nb; ra.Nh = Nh; ra.B = B; ra.nsplit = pl.nsplit;
+    ra.ntiles_blue = pl.ntiles_blue; ra.ntiles = pl.t.npt;
+    size_t n_pl = part_len(P, Nb, Nh);
+    k_reduce<float><<<(int)((n_pl + 255) / 256), 256, 0, st>>>(ra);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int qfa_train_accumulate(const QfaModel* model, const float* delta, const float* error,
                                     const float* zabs, const uint8_t* mask, int B, void* workspace,
                                     size_t workspace_bytes, void* acc, void* nll_per_spectrum, int precision,
@@ -260,6 +357,13 @@ extern "C" int qfa_train_accumulate(const QfaModel* model, const float* delta, c
         return fail(QFA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total, workspace_bytes);
     if (((uintptr_t)workspace & 255) != 0) return fail(QFA_ERR_ALIGN, "workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    if (tc_use(model->Nh, precision, B, flags)) {
+        TcTrainPlan tp = plan_tc_train(model->Nb, model->Nr, model->Nh, B);
+        if (B > 0 && workspace_bytes < tp.total)
+            return fail(QFA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", tp.total, workspace_bytes);
+        return train_accumulate_tc(model, delta, error, zabs, mask, B, (char*)workspace, tp, (float*)acc,
+                                   (float*)nll_per_spectrum, flags, st);
+    }
     if (precision == QFA_PREC_FP64)
         return train_accumulate_t<double>(model, delta, error, zabs, mask, B, (char*)workspace, pl, (double*)acc,
                                           (double*)nll_per_spectrum, flags, st);
@@ -312,7 +416,6 @@ extern "C" int qfa_predict(const QfaModel* model, const float* flux, const float
                            const uint8_t* mask, int B, void* workspace, size_t workspace_bytes, void* nll,
                            void* hmean, void* hcov, void* cont, void* unc, int precision, int flags,
                            void* stream) {
-    (void)workspace; (void)workspace_bytes; (void)flags;
     int rc = check_model(model, precision);
     if (rc) return rc;
     if (B < 0) return fail(QFA_ERR_SHAPE, "B=%d", B);
@@ -321,7 +424,7 @@ extern "C" int qfa_predict(const QfaModel* model, const float* flux, const float
     if (!nll) return fail(QFA_ERR_NULL, "nll is NULL");
     if (!flux || !error || !mask || (!zabs && model->Nb > 0)) return fail(QFA_ERR_NULL, "flux/error/zabs/mask is NULL");
     cudaStream_t st = (cudaStream_t)stream;
-    if (tc_eligible(model->Nh, precision)) {
+    if (tc_use(model->Nh, precision, B, flags)) {
         const bool want_o = cont || unc;
         TcPlan pl = plan_tc(model->Nb, model->Nr, B, true);
         if (!workspace || workspace_bytes < pl.total)

@@ -142,9 +142,11 @@ struct GramCfg {
     static constexpr int NW = TRAIN ? 4 : 2;                   // weight arrays per chunk
     static constexpr int NACC = TRAIN ? 40 : 20;               // accumulators per thread
     static constexpr int LD = HP + 1;
-    static constexpr size_t smem_elems =
-        (size_t)PC * HP + (size_t)NW * PC + (size_t)NACC * NT + 3 * HP * LD + 4 * HP + 4 * 32 + 8;
-    static constexpr size_t smem_bytes = smem_elems * sizeof(T);
+    // streaming part in T, the per-spectrum H x H algebra always in double (its cost is negligible and it removes the
+    // factorisation error: what is left in float mode is the rounding of the Gram entries themselves)
+    static constexpr size_t smem_stream = ((size_t)PC * HP + (size_t)NW * PC + (size_t)NACC * NT + 4 * 32) * sizeof(T);
+    static constexpr size_t smem_alg = (3 * (size_t)HP * LD + 4 * HP + 8) * sizeof(double);
+    static constexpr size_t smem_bytes = ((smem_stream + 15) / 16) * 16 + smem_alg;
 };
 
 template <typename T, int HP, int MODE>
@@ -154,18 +156,19 @@ __global__ void __launch_bounds__(256) k_gram_solve(GramArgs<T> g) {
     constexpr bool TRAIN = C::TRAIN;
     constexpr bool PREDICT = (MODE == MODE_PREDICT);
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    using TA = double;                          // algebra type
     T* sF = reinterpret_cast<T*>(smem_raw);     // [PC][HP]
     T* sW = sF + PC * HP;                       // [NW][PC]
     T* sPart = sW + C::NW * PC;                 // [NACC][NT]
-    T* sM = sPart + NACC * NT;                  // [HP][LD]
-    T* sM2 = sM + HP * LD;
-    T* sL = sM2 + HP * LD;
-    T* sb = sL + HP * LD;
-    T* sb2 = sb + HP;
-    T* sa = sb2 + HP;
-    T* sc = sa + HP;
-    T* sred = sc + HP;                          // [4*32]
-    T* sout = sred + 4 * 32;                    // [8]
+    T* sred = sPart + NACC * NT;                // [4*32]
+    TA* sM = reinterpret_cast<TA*>(smem_raw + ((C::smem_stream + 15) / 16) * 16);   // [HP][LD]
+    TA* sM2 = sM + HP * LD;
+    TA* sL = sM2 + HP * LD;
+    TA* sb = sL + HP * LD;
+    TA* sb2 = sb + HP;
+    TA* sa = sb2 + HP;
+    TA* sc = sa + HP;
+    TA* sout = sc + HP;                         // [8]
 
     const Field<T>& f = g.f;
     const int tid = threadIdx.x;
@@ -280,13 +283,13 @@ __global__ void __launch_bounds__(256) k_gram_solve(GramArgs<T> g) {
             while (rem >= C::NB1 - kb) { rem -= C::NB1 - kb; ++kb; }
             const int lb = kb + rem;
             const int jj = (j >= 20) ? j - 20 : j;
-            T* dstM = (j >= 20) ? sM2 : sM;
-            T* dstb = (j >= 20) ? sb2 : sb;
+            TA* dstM = (j >= 20) ? sM2 : sM;
+            TA* dstb = (j >= 20) ? sb2 : sb;
             if (jj < 16) {
                 const int q = jj / 4, r = jj % 4;
                 const int row = 4 * kb + q, col = 4 * lb + r;
                 if (kb != lb || q <= r) {
-                    const T v = s + ((j < 20 && row == col) ? T(1) : T(0));   // M = I + Gram
+                    const TA v = (TA)s + ((j < 20 && row == col) ? TA(1) : TA(0));   // M = I + Gram
                     dstM[row * LD + col] = v;
                     dstM[col * LD + row] = v;
                 }
@@ -295,33 +298,33 @@ __global__ void __launch_bounds__(256) k_gram_solve(GramArgs<T> g) {
             }
         }
         __syncthreads();
-        if (tid < 32) small_algebra<T, HP, TRAIN>(sM, sM2, sL, sb, sb2, sa, sc, sout);
+        if (tid < 32) small_algebra<TA, HP, TRAIN>(sM, sM2, sL, sb, sb2, sa, sc, sout);
         __syncthreads();
 
         // ---- per-spectrum outputs
         if (tid == 0) {
             // model.py:135 / 176; n*log(2 pi) kept in T (quirk Q5 is below the 1e-5 bar)
-            T nll = T(0.5) * (sums[0] - sout[1] + sums[2] * T(kLog2Pi) + sums[1] + sout[0]);
-            g.nll[b] = nll;
+            TA nll = TA(0.5) * ((TA)sums[0] - sout[1] + (TA)sums[2] * TA(kLog2Pi) + (TA)sums[1] + sout[0]);
+            g.nll[b] = (T)nll;
             if (TRAIN) g.hasblue[b] = sums[3] > T(0) ? 1.0f : 0.0f;
         }
         if (TRAIN) {
             using SL = SmallLayout<HP>;
             T* dst = g.small + (size_t)b * SL::len;
             for (int e = tid; e < SL::len; e += NT) {
-                T v;
+                TA v;
                 if (e < SL::c) v = sa[e];
                 else if (e < SL::Linv) v = sc[e - SL::c];
                 else if (e < SL::K) { int t = e - SL::Linv; v = sL[(t / HP) * LD + (t % HP)]; }
                 else { int t = e - SL::K; v = sM2[(t / HP) * LD + (t % HP)]; }
-                dst[e] = v;
+                dst[e] = (T)v;
             }
         }
         if (PREDICT) {
-            if (g.hmean && tid < Nh) g.hmean[(size_t)b * Nh + tid] = sa[tid];
+            if (g.hmean && tid < Nh) g.hmean[(size_t)b * Nh + tid] = (T)sa[tid];
             if (g.hcov)
                 for (int e = tid; e < Nh * Nh; e += NT)
-                    g.hcov[(size_t)b * Nh * Nh + e] = sM[(e / Nh) * LD + (e % Nh)];
+                    g.hcov[(size_t)b * Nh * Nh + e] = (T)sM[(e / Nh) * LD + (e % Nh)];
             if (g.cont || g.unc) {
                 // model.py:180: mu + F hmean and sqrt(diag(F hcov F^T)) on the FULL grid
                 for (int i = tid; i < P; i += NT) {
@@ -331,10 +334,10 @@ __global__ void __launch_bounds__(256) k_gram_solve(GramArgs<T> g) {
                     T fa = T(0), q = T(0);
 #pragma unroll
                     for (int k = 0; k < HP; ++k) {
-                        fa += fr[k] * sa[k];
+                        fa += fr[k] * (T)sa[k];
                         T y = T(0);
 #pragma unroll
-                        for (int l = 0; l <= k; ++l) y += sL[k * LD + l] * fr[l];   // y = L^-1 f
+                        for (int l = 0; l <= k; ++l) y += (T)sL[k * LD + l] * fr[l];   // y = L^-1 f
                         q += y * y;
                     }
                     if (g.cont) g.cont[(size_t)b * P + i] = (T)__ldg(f.mu + i) + fa;

@@ -107,6 +107,10 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int k) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + ((k & 3) << 2));
 }
 
+inline uint32_t sw128_offset_host(int r, int k) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + ((k & 3) << 2));
+}
+
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
     return (1u << 4)                        // D format  : F32
            | (2u << 7)                      // A format  : TF32

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import QfaError, QfaModelStruct, PRECISIONS, FLAG_ZERO_ACC
+from ._lib import QfaError, QfaModelStruct, PRECISIONS, FLAG_ZERO_ACC, FLAG_FORCE_TENSOR
 from .utils import default_tau, resolve_tau_law
 
 log2pi = 1.8378770664093453  # reference model.py:20
@@ -158,6 +158,10 @@ class QFA(object):
         return PRECISIONS[self.precision]
 
     @property
+    def _flags(self):
+        return FLAG_FORCE_TENSOR if self.precision == "tf32" else 0
+
+    @property
     def _tdtype(self):
         return torch.float64 if self.precision == "fp64" else torch.float32
 
@@ -221,7 +225,7 @@ class QFA(object):
         st = self._struct()
         _lib.check(L.qfa_train_accumulate(ctypes.byref(st), _ptr(delta), _ptr(error), _ptr(zabs), _ptr(mask), B,
                                           _ptr(ws), ws.numel(), _ptr(self._acc), _ptr(nll_out), self._prec,
-                                          FLAG_ZERO_ACC if zero else 0, self._stream()), "qfa_train_accumulate")
+                                          (FLAG_ZERO_ACC if zero else 0) | self._flags, self._stream()), "qfa_train_accumulate")
         return self._acc
 
     def finalize(self, acc=None):
@@ -276,7 +280,7 @@ class QFA(object):
         ws = self._workspace(L.qfa_predict_workspace_bytes(self.Nb, self.Nr, self.Nh, B, self._prec))
         _lib.check(L.qfa_predict(ctypes.byref(st), _ptr(flux), _ptr(error), _ptr(zabs), _ptr(mask), B, _ptr(ws),
                                  ws.numel(), _ptr(out["nll"]), _ptr(out.get("hmean")), _ptr(out.get("hcov")),
-                                 _ptr(out.get("cont")), _ptr(out.get("unc")), self._prec, 0, self._stream()),
+                                 _ptr(out.get("cont")), _ptr(out.get("unc")), self._prec, self._flags, self._stream()),
                    "qfa_predict")
 
     # ------------------------------------------------------------------ host-buffer (end-to-end) paths

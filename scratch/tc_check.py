@@ -14,7 +14,7 @@ for name in CASES:
     Npix, Nh = c["F"].shape
     if Nh > 8: continue
     m = QFA(c["Nb"], Npix - c["Nb"], Nh, torch.device("cuda:0"), tau=c["law"],
-            model_params={k: c[k] for k in ("F", "Psi", "omega", "tau0", "c0", "beta")}, precision="mixed")
+            model_params={k: c[k] for k in ("F", "Psi", "omega", "tau0", "c0", "beta")}, precision="tf32")
     m.mu = torch.tensor(c["mu"])
     o = m.predict_batch(d(c["flux"]), d(c["error"]), d(c["zabs"]), d(c["mask"]))
     torch.cuda.synchronize()

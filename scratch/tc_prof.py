@@ -10,7 +10,7 @@ Bn = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 128
 mode = sys.argv[2] if len(sys.argv) > 2 else "predict"
 data = synth.make_spectra(P, mu, grid, Bn, seed=1234, device=torch.device("cuda:0"))
 Pn = {key: v.numpy() for key, v in P.items()}
-m = QFA(grid.Nb, grid.Nr, 8, torch.device("cuda:0"), model_params=Pn, precision="mixed"); m.mu = mu
+m = QFA(grid.Nb, grid.Nr, 8, torch.device("cuda:0"), model_params=Pn, precision="tf32"); m.mu = mu
 X, E, Z, M = data["flux"], data["error"], data["zabs"], data["mask"].view(torch.uint8)
 if mode == "predict":
     o = m.predict_batch(X, E, Z, M)

@@ -109,8 +109,80 @@ def test_float_modes_against_fp64_golden(name, precision, cuda_model_factory):
         assert relerr(grads[k].cpu().numpy(), g["grad_" + k]) < 5e-2, k
 
 
+# ----------------------------------------------------------------------------- tensor-core kernels
+TC_CASES = tuple(n for n in CASES if n not in ("l32", "tiny12", "tiny16"))      # Nh <= 8
+
+
+@pytest.mark.parametrize("name", TC_CASES)
+def test_tensor_core_path_against_fp64_golden(name, cuda_model_factory):
+    """precision="tf32" forces the tcgen05 kernels (k_tc_gram / k_tc_grad) even for these tiny batches.
+    Operands are rounded to TF32 (2^-11 relative), accumulation is fp32 in TMEM.  On the reference's own model
+    ('sdss': pretrained parameters, 1913 pixels) the stated mixed-mode bar holds: continuum <= 1e-3.  The tiny
+    cases are random unit-scale factor matrices on 96 pixels: far fewer pixels to average the operand rounding
+    over and a worse-conditioned M = I + F^T D^-1 F, so the error is amplified; they pin correctness of the
+    kernels (edge shapes, padding of Nh, masks), with bounds that still catch any indexing / protocol bug."""
+    c, g = load_case(name, "f64")
+    m = cuda_model_factory(c, "tf32")
+    real = name == "sdss"
+    o = m.predict_batch(dev(c["flux"]), dev(c["error"]), dev(c["zabs"]), dev(c["mask"]))
+    assert relerr(o["cont"].cpu().numpy(), g["pred_cont"]) < (1e-3 if real else 5e-3)
+    assert relerr(o["unc"].cpu().numpy(), g["pred_unc"]) < (1e-3 if real else 3e-2)
+    assert relerr(o["hmean"].cpu().numpy(), g["pred_hmean"]) < (2e-3 if real else 4e-2)
+    assert relerr(o["hcov"].cpu().numpy(), g["pred_hcov"]) < (2e-3 if real else 4e-2)
+    npx = np.maximum(1, c["mask"].sum(1))
+    assert np.all(np.abs(o["nll"].cpu().numpy() - g["pred_nll"]) <= (1e-3 if real else 1e-2) * npx)
+    nll_only = m.nll_batch(dev(c["flux"]), dev(c["error"]), dev(c["zabs"]), dev(c["mask"]))
+    assert torch.equal(nll_only, o["nll"])                     # scoring mode = same kernel without phase O
+    loss, grads = m.forward(dev(c["delta"]), dev(c["error"]), dev(c["zabs"]), dev(c["mask"]))
+    assert abs(float(loss) - float(np.squeeze(g["loss"]))) <= (1e-3 if real else 1e-2) * npx.mean()
+    for k in KEYS:
+        assert relerr(grads[k].cpu().numpy(), g["grad_" + k]) < 5e-2, k       # incl. NaN placement (0/0)
+
+
+def test_tensor_core_path_ragged_tiles_and_properties():
+    """SDSS shape (1913 pixels = 59.8 K-blocks = 14.9 pixel tiles), 300 + 5 spectra (2 full 128-tiles + 44, then a
+    5-spectrum tile): tensor-core results per spectrum do not depend on the tile they fall in, masked garbage is
+    ignored, repetition is bitwise identical, and everything agrees with the fp64 kernels."""
+    from qfa_b200 import QFA
+    grid, P, mu, d = _synthetic("sdss", 8, 305, 99, _sdss_pretrained())
+    Pn = {k: v.numpy() for k, v in P.items()}
+    mt = QFA(grid.Nb, grid.Nr, 8, torch.device("cuda:0"), model_params=Pn, precision="tf32")
+    m64 = QFA(grid.Nb, grid.Nr, 8, torch.device("cuda:0"), model_params=Pn, precision="fp64")
+    mt.mu = mu; m64.mu = mu
+    X, D, E, Z, M = (d[k].cuda() for k in ("flux", "delta", "error", "zabs", "mask"))
+    o = mt.predict_batch(X, E, Z, M)
+    r = m64.predict_batch(X, E, Z, M)
+    assert relerr(o["cont"].cpu().numpy(), r["cont"].cpu().numpy()) < 1e-3
+    assert relerr(o["unc"].cpu().numpy(), r["unc"].cpu().numpy()) < 1e-3
+    assert relerr(o["hmean"].cpu().numpy(), r["hmean"].cpu().numpy()) < 2e-3
+    npx = np.maximum(1, M.sum(1).cpu().numpy())
+    assert np.all(np.abs(o["nll"].cpu().numpy() - r["nll"].cpu().numpy()) <= 1e-3 * npx)
+    # a spectrum's outputs are independent of its position in the batch / tile
+    o5 = mt.predict_batch(X[300:], E[300:], Z[300:], M[300:])
+    for k in ("nll", "hmean", "cont", "unc"):
+        assert torch.equal(o5[k], o[k][300:]), k
+    full = mt.accumulate(D, E, Z, M).clone()
+    ref = m64.accumulate(D, E, Z, M).double().cpu().numpy()
+    a, b = split_acc(mt, full), split_acc(m64, torch.as_tensor(ref))
+    assert np.array_equal(a["pix_cnt"], b["pix_cnt"]) and np.array_equal(a["scal_cnt"], b["scal_cnt"])
+    assert abs(a["nll_sum"] - b["nll_sum"]) <= 1e-4 * abs(b["nll_sum"])
+    n_f = mt.Npix * mt.Nh
+    assert relerr(a["sums"][:n_f], b["sums"][:n_f]) < 2e-2
+    assert relerr(a["sums"][n_f:n_f + mt.Npix], b["sums"][n_f:n_f + mt.Npix]) < 5e-3          # Psi
+    assert relerr(a["dmu"], b["dmu"]) < 5e-3
+    D2, E2 = D.clone(), E.clone()
+    D2[~M] = float("nan")
+    E2[~M] = float("inf")
+    assert torch.equal(mt.accumulate(D2, E2, Z, M), full)
+    assert torch.equal(mt.accumulate(D, E, Z, M), full)
+    h = 128
+    a0 = mt.accumulate(D[:h], E[:h], Z[:h], M[:h]).clone()
+    a1 = mt.accumulate(D[h:], E[h:], Z[h:], M[h:]).clone()
+    assert relerr((a0 + a1).cpu().numpy(), full.cpu().numpy()) < 2e-4
+
+
 # ----------------------------------------------------------------------------- shipped known answer
-@pytest.mark.parametrize("precision", ["fp64", "fp32", "mixed"])
+@pytest.mark.parametrize("precision", ["fp64", "fp32", "mixed", "tf32"])
 def test_shipped_known_answer_vector(precision, tmp_path):
     """BASELINE config 1: data/spec-4321-55504-0114.npz with data/model_parameters.npz
     (nb/predict.ipynb cells 4, 9, 10) -> ll = -510.229248, ll_red = -791.925537."""
@@ -195,7 +267,7 @@ def test_fp64_against_lowrank_oracle_seeded(shape):
     assert relerr(o["unc"].cpu().numpy(), runc) < 1e-7
     assert relerr(o["hcov"].cpu().numpy(), rc) < 1e-7
     # float modes on the same inputs: continuum bar 1e-3
-    for prec in ("fp32", "mixed"):
+    for prec in ("fp32", "mixed") + (("tf32",) if shape != "l32" else ()):
         m.precision = prec
         m._acc = None
         of = m.predict_batch(d["flux"].cuda(), d["error"].cuda(), d["zabs"].cuda(), d["mask"].cuda())
@@ -204,7 +276,7 @@ def test_fp64_against_lowrank_oracle_seeded(shape):
 
 
 # ----------------------------------------------------------------------------- properties at full size
-@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("precision", ["fp64", "fp32", "mixed"])
 def test_properties_at_baseline_size(precision):
     """SDSS shape, 6000 spectra (spans several sub-batches): results do not depend on how the batch is
     split (data-parallel == single GPU), on the order of the spectra, or on what is stored
@@ -249,6 +321,12 @@ def test_properties_at_baseline_size(precision):
     m.accumulate(D[:512], E[:512], Z[:512], M[:512], nll_out=nll)
     # (delta is stored as float32, so the two paths see inputs that differ by one float32 rounding)
     assert relerr(o["nll"].cpu().numpy(), nll.cpu().numpy()) < (1e-6 if precision == "fp64" else 2e-3)
+    if precision == "mixed":      # 6000 >= QFA_TC_MIN_BATCH: this ran on the tensor-core kernels; tie it to fp64
+        m64 = QFA(grid.Nb, grid.Nr, 8, torch.device("cuda:0"), model_params=Pn, precision="fp64")
+        r = split_acc(m64, m64.accumulate(D, E, Z, M))
+        n_f = m.Npix * m.Nh
+        assert relerr(a["sums"][:n_f], r["sums"][:n_f]) < 2e-2 and relerr(a["dmu"], r["dmu"]) < 5e-3
+        assert abs(a["nll_sum"] - r["nll_sum"]) <= 1e-4 * abs(r["nll_sum"])
 
 
 def test_empty_and_ragged_batches():
