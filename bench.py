@@ -51,7 +51,7 @@ def parse():
 WORKLOADS = {
     # name: (grid, Nh, kind, default spectra per GPU, cpu sample)
     "sdss100k_predict": ("sdss", 8, "predict", 100_000, 192),
-    "sdss_train": ("sdss", 8, "train", 65_536, 64),
+    "sdss_train": ("sdss", 8, "train", 75_776, 64),        # 148 SMs x 4 waves x 128-spectra tiles
     "l32_train": ("l32", 32, "train", 65_536, 256),
     "desi_score": ("desi", 8, "score", 32_768, 4),
 }
@@ -233,8 +233,14 @@ def measure_workload(name, args, rank, world, peaks, want_e2e, want_cpu, nspec_o
             acc = m.accumulate(X, E, Z, M, zero=True)
             m._allreduce(acc)
             opt.update_from_acc(m, acc)
-        n_sub = -(-nspec // max(1, min(nspec, (48 << 20) // (9 * grid.Npix + 4 * grid.Nb))))
-        launches_per_step = 2 * n_sub + 1 + 1
+        if Nh <= 8 and args.precision == "mixed":
+            # k_tc_build_images, k_tc_gram<TRAIN>, k_tc_grad, k_reduce, k_adam
+            launches_per_step = 5
+            kernel_name = "k_tc_gram<TRAIN> + k_tc_grad (tcgen05) + k_reduce + k_adam"
+        else:
+            n_sub = -(-nspec // max(1, min(nspec, (48 << 20) // (9 * grid.Npix + 4 * grid.Nb))))
+            launches_per_step = 2 * n_sub + 1 + 1
+            kernel_name = "k_gram_solve + k_grad (CUDA cores) + k_reduce + k_adam"
     else:
         want = ("nll", "hmean", "hcov", "cont", "unc") if kind == "predict" else ("nll",)
         outs = {"nll": torch.empty(nspec, device=dev)}
@@ -246,7 +252,12 @@ def measure_workload(name, args, rank, world, peaks, want_e2e, want_cpu, nspec_o
 
         def step():
             m.predict_into(X, E, Z, M, outs)
-        launches_per_step = 1
+        if Nh <= 8 and args.precision == "mixed":
+            launches_per_step = 2          # k_tc_build_images, k_tc_gram<PREDICT>
+            kernel_name = "k_tc_gram<PREDICT> (tcgen05 Gram GEMM + solve + continuum GEMM)"
+        else:
+            launches_per_step = 1
+            kernel_name = "k_gram_solve (CUDA cores)"
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
     ms, t0, t1 = timed(step, args.steps, args.warmup, world)
     clocks = sampler.stop(t0, t1) if sampler else None
@@ -258,7 +269,7 @@ def measure_workload(name, args, rank, world, peaks, want_e2e, want_cpu, nspec_o
     res.update(value=value, ms_per_step=ms / args.steps, clocks=clocks, gpu_launches=launches_per_step * args.steps,
                roofline={"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": None,
-                         "kernel": "k_gram_solve (predict)" if kind != "train" else "k_gram_solve + k_grad (train step)",
+                         "kernel": kernel_name,
                          "bytes_per_spectrum": bps, "peak_source": peaks["source"]},
                config={"workload": name, "kind": kind, "grid": grid_name, "Npix": grid.Npix, "Nb": grid.Nb, "Nh": Nh,
                        "spectra_per_gpu_per_step": nspec, "precision": args.precision,

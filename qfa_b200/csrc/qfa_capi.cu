@@ -110,11 +110,12 @@ static TrainPlan plan_train(int Nb, int Nr, int Nh, int B, int precision) {
 // ---- tensor-core path (QFA_PREC_TF32, Nh <= 8): static operand images live in the workspace
 struct TcPlan {
     int nkb, npt, ntiles;
+    tcg::TileSched ts;
     size_t off_pb, off_qa, total;
 };
 static inline bool tc_eligible(int Nh, int precision) { return precision == QFA_PREC_TF32 && Nh <= tcg::HP; }
-// The tensor-core kernels work on tiles of 128 spectra; below this batch size the float CUDA-core kernels
-// (one CTA per spectrum) fill the GPU better.  QFA_FLAG_FORCE_TENSOR overrides (tests, small-batch profiling).
+// The tensor-core kernels work on tiles of up to 128 spectra per CTA; below this batch size the float CUDA-core
+// kernels (one CTA per spectrum) fill the GPU better.  QFA_FLAG_FORCE_TENSOR overrides (tests, profiling).
 static int tc_min_batch() {
     static int v = -1;
     if (v < 0) {
@@ -127,12 +128,35 @@ static int tc_min_batch() {
 static inline bool tc_use(int Nh, int precision, int B, int flags) {
     return tc_eligible(Nh, precision) && (B >= tc_min_batch() || (flags & QFA_FLAG_FORCE_TENSOR));
 }
-static TcPlan plan_tc(int Nb, int Nr, int B, bool want_qa) {
+
+// Tile heights: the tile count should be a whole number of waves of num_sms() persistent CTAs.  Heights are
+// multiples of `quantum` (16: rows are dealt round-robin to the 16 warps of a CTA; 32 for the train path, whose
+// gradient kernel walks the tiles in 32-spectra chunks); n_hi tiles are one quantum taller than the others.
+static tcg::TileSched tile_sched(int B, int quantum, int* ntiles) {
+    tcg::TileSched ts;
+    const long nsm = num_sms();
+    if (B <= 0) { ts.r_hi = ts.r_lo = tcg::TS; ts.n_hi = 0; *ntiles = 0; return ts; }
+    const long waves = ((long)B + nsm * tcg::TS - 1) / (nsm * tcg::TS);
+    const long slots = nsm * waves;
+    long r_lo = (B / slots) / quantum * quantum;
+    if (r_lo < quantum) r_lo = quantum;
+    long r_hi = r_lo + quantum > tcg::TS ? tcg::TS : r_lo + quantum;
+    long rest = (long)B - slots * r_lo;
+    long n_hi = (rest > 0 && r_hi > r_lo) ? (rest + (r_hi - r_lo) - 1) / (r_hi - r_lo) : 0;
+    if (n_hi > slots) n_hi = slots;
+    ts.r_hi = (int)r_hi; ts.r_lo = (int)r_lo; ts.n_hi = (int)n_hi;
+    long covered = n_hi * r_hi, t = n_hi;
+    if (covered < B) t += ((long)B - covered + r_lo - 1) / r_lo;
+    else t = ((long)B + r_hi - 1) / r_hi;
+    *ntiles = (int)t;
+    return ts;
+}
+static TcPlan plan_tc(int Nb, int Nr, int B, bool want_qa, int quantum = 1) {
     TcPlan p;
     const int P = Nb + Nr;
     p.nkb = (P + tcg::KB - 1) / tcg::KB;
     p.npt = (P + tcg::PT - 1) / tcg::PT;
-    p.ntiles = (B + tcg::TS - 1) / tcg::TS;
+    p.ts = tile_sched(B, quantum < 16 ? 16 : quantum, &p.ntiles);
     size_t o = 0;
     p.off_pb = o; o = align_up(o + (size_t)p.nkb * tcg::PB_TILE, 1024);
     p.off_qa = o; if (want_qa) o = align_up(o + (size_t)p.npt * tcg::QA_TILE, 1024);
@@ -142,13 +166,13 @@ static TcPlan plan_tc(int Nb, int Nr, int B, bool want_qa) {
 struct TcTrainPlan {
     TcPlan t;
     int nchunks, nsplit, ntiles_blue;
-    size_t off_b2, off_kc, off_hasblue, off_nll, off_part, off_spart, total;
+    size_t off_b2, off_kc, off_tsums, off_part, off_spart, total;
 };
 static TcTrainPlan plan_tc_train(int Nb, int Nr, int Nh, int B) {
     TcTrainPlan p;
     const int P = Nb + Nr;
-    p.t = plan_tc(Nb, Nr, B, true);
-    p.nchunks = (B + tcg::GC - 1) / tcg::GC;
+    p.t = plan_tc(Nb, Nr, B, true, tcg::GC);
+    p.nchunks = p.t.ntiles * 4;
     int ns = num_sms() / p.t.npt;
     if (ns > p.nchunks) ns = p.nchunks;
     if (ns < 1) ns = 1;
@@ -158,8 +182,7 @@ static TcTrainPlan plan_tc_train(int Nb, int Nr, int Nh, int B) {
     o = align_up(o, 1024);
     p.off_b2 = o;      o = align_up(o + (size_t)p.t.ntiles * tcg::B2_TILE, 1024);
     p.off_kc = o;      o = align_up(o + (size_t)p.t.ntiles * 4 * tcg::KC_TILE, 1024);
-    p.off_hasblue = o; o = align_up(o + (size_t)(B > 0 ? B : 1) * 4, 256);
-    p.off_nll = o;     o = align_up(o + (size_t)(B > 0 ? B : 1) * 4, 256);
+    p.off_tsums = o;   o = align_up(o + (size_t)(p.t.ntiles > 0 ? p.t.ntiles : 1) * 4 * 2 * 4, 256);
     p.off_part = o;    o = align_up(o + (size_t)p.nsplit * part_len(P, Nb, Nh) * 4, 256);
     p.off_spart = o;   o = align_up(o + (size_t)p.nsplit * p.t.npt * 3 * 4, 256);
     p.total = o;
@@ -283,7 +306,7 @@ static int train_accumulate_t(const QfaModel* m, const float* delta, const float
     }
     ReduceArgs<T> ra;
     ra.part = part; ra.spart = spart; ra.nll = nll; ra.hasblue = hasblue; ra.scal = make_field<T>(m, 0, 0, 0, 0).scal;
-    ra.acc = acc; ra.P = P; ra.Nb = Nb; ra.Nh = Nh; ra.B = B; ra.nsplit = nsplit_used;
+    ra.acc = acc; ra.P = P; ra.Nb = Nb; ra.Nh = Nh; ra.B = B; ra.stride = 1; ra.nsp = (double)B; ra.nsplit = nsplit_used;
     ra.ntiles_blue = pl.ntiles_blue; ra.ntiles = pl.ntiles;
     size_t n_el = part_len(P, Nb, Nh);
     int blocks = (int)((n_el + 255) / 256);
@@ -303,8 +326,7 @@ static int train_accumulate_tc(const QfaModel* m, const float* delta, const floa
     float* QA = reinterpret_cast<float*>(ws + pl.t.off_qa);
     float* sm_b2 = reinterpret_cast<float*>(ws + pl.off_b2);
     float* sm_kc = reinterpret_cast<float*>(ws + pl.off_kc);
-    float* hasblue = reinterpret_cast<float*>(ws + pl.off_hasblue);
-    float* nll = nll_out ? nll_out : reinterpret_cast<float*>(ws + pl.off_nll);
+    float* tsums = reinterpret_cast<float*>(ws + pl.off_tsums);
     float* part = reinterpret_cast<float*>(ws + pl.off_part);
     float* spart = reinterpret_cast<float*>(ws + pl.off_spart);
     const size_t n_el = (size_t)pl.t.nkb * PB_ROWS * KB + (size_t)pl.t.npt * 2 * PT * KB;
@@ -320,22 +342,22 @@ static int train_accumulate_tc(const QfaModel* m, const float* delta, const floa
     }
     Field<float> f = make_field<float>(m, delta, error, zabs, mask);
     TcGramArgs a;
-    a.f = f; a.B = B; a.ntiles = pl.t.ntiles; a.nkb = pl.t.nkb; a.npt = pl.t.npt;
-    a.PB = PB; a.QA = QA; a.nll = nll; a.hmean = nullptr; a.hcov = nullptr; a.cont = nullptr; a.unc = nullptr;
-    a.sm_b2 = sm_b2; a.sm_kc = sm_kc; a.hasblue = hasblue;
+    a.f = f; a.B = B; a.ts = pl.t.ts; a.ntiles = pl.t.ntiles; a.nkb = pl.t.nkb; a.npt = pl.t.npt;
+    a.PB = PB; a.QA = QA; a.nll = nll_out; a.hmean = nullptr; a.hcov = nullptr; a.cont = nullptr; a.unc = nullptr;
+    a.sm_b2 = sm_b2; a.sm_kc = sm_kc; a.hasblue = nullptr; a.tile_sums = tsums;
     int grid = pl.t.ntiles < num_sms() ? pl.t.ntiles : num_sms();
     k_tc_gram<TC_TRAIN><<<grid, NTHREADS, Cfg<TC_TRAIN>::SMEM_BYTES, st>>>(a);
     CK(cudaGetLastError());
     TcGradArgs ga;
-    ga.f = f; ga.B = B; ga.nchunks = pl.nchunks; ga.nsplit = pl.nsplit; ga.QA = QA; ga.sm_b2 = sm_b2; ga.sm_kc = sm_kc;
+    ga.f = f; ga.B = B; ga.ts = pl.t.ts; ga.nchunks = pl.nchunks; ga.nsplit = pl.nsplit; ga.QA = QA; ga.sm_b2 = sm_b2; ga.sm_kc = sm_kc;
     ga.zero = reinterpret_cast<const uint8_t*>(PB) + sw128_offset_host(36, 0);
     ga.part = part; ga.spart = spart; ga.accumulate = 0;
     k_tc_grad<<<dim3(pl.t.npt, pl.nsplit), NTHREADS, GradSmem::BYTES, st>>>(ga);
     CK(cudaGetLastError());
     ReduceArgs<float> ra;
-    ra.part = part; ra.spart = spart; ra.nll = nll; ra.hasblue = hasblue; ra.scal = f.scal;
-    ra.acc = acc; ra.P = P; ra.Nb = Nb; ra.Nh = Nh; ra.B = B; ra.nsplit = pl.nsplit;
-    ra.ntiles_blue = pl.ntiles_blue; ra.ntiles = pl.t.npt;
+    ra.part = part; ra.spart = spart; ra.nll = tsums; ra.hasblue = tsums + 1; ra.scal = f.scal;   // pre-folded per 32 rows
+    ra.acc = acc; ra.P = P; ra.Nb = Nb; ra.Nh = Nh; ra.B = pl.t.ntiles * 4; ra.stride = 2; ra.nsp = (double)B;
+    ra.nsplit = pl.nsplit; ra.ntiles_blue = pl.ntiles_blue; ra.ntiles = pl.t.npt;
     size_t n_pl = part_len(P, Nb, Nh);
     k_reduce<float><<<(int)((n_pl + 255) / 256), 256, 0, st>>>(ra);
     CK(cudaGetLastError());
@@ -403,9 +425,9 @@ static int predict_tc(const QfaModel* m, const float* flux, const float* error, 
     }
     TcGramArgs a;
     a.f = make_field<float>(m, flux, error, zabs, mask);
-    a.B = B; a.ntiles = pl.ntiles; a.nkb = pl.nkb; a.npt = pl.npt;
+    a.B = B; a.ts = pl.ts; a.ntiles = pl.ntiles; a.nkb = pl.nkb; a.npt = pl.npt;
     a.PB = PB; a.QA = QA; a.nll = nll; a.hmean = hmean; a.hcov = hcov; a.cont = cont; a.unc = unc;
-    a.sm_b2 = nullptr; a.sm_kc = nullptr; a.hasblue = nullptr;
+    a.sm_b2 = nullptr; a.sm_kc = nullptr; a.hasblue = nullptr; a.tile_sums = nullptr;
     int grid = pl.ntiles < num_sms() ? pl.ntiles : num_sms();
     k_tc_gram<TC_PREDICT><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(a);
     CK(cudaGetLastError());

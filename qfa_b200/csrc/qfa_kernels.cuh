@@ -482,7 +482,9 @@ template <typename T>
 struct ReduceArgs {
     const T* part; const T* spart; const T* nll; const float* hasblue; const float* scal;
     T* acc;
-    int P, Nb, Nh, B, nsplit, ntiles_blue, ntiles;
+    int P, Nb, Nh, B, nsplit, ntiles_blue, ntiles;   // B = length of nll / hasblue (per spectrum, or pre-folded partial sums)
+    int stride;                                       // element stride of nll / hasblue
+    double nsp;                                       // number of spectra these sums stand for
 };
 
 template <typename T>
@@ -507,7 +509,10 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs<T> r) {
         // last block additionally folds the per-spectrum scalars (block-strided, fixed tree)
         __shared__ T red[4 * 32];
         T v[2] = {T(0), T(0)};
-        for (int b = threadIdx.x; b < r.B; b += blockDim.x) { v[0] += r.nll[b]; v[1] += (T)r.hasblue[b]; }
+        for (int b = threadIdx.x; b < r.B; b += blockDim.x) {
+            v[0] += r.nll[(size_t)b * r.stride];
+            v[1] += (T)r.hasblue[(size_t)b * r.stride];
+        }
         block_sum<T, 2, 256>(v, red);
         T s3[3] = {T(0), T(0), T(0)};
         const int nsp = r.nsplit * r.ntiles;
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs<T> r) {
             r.acc[o_scnt + 1] += v[1];                                  // c0
             r.acc[o_scnt + 2] += (tau0 != T(0)) ? v[1] : T(0);          // beta: every term carries tau0
             r.acc[o_nll] += v[0];
-            r.acc[o_nsp] += (T)r.B;
+            r.acc[o_nsp] += (T)r.nsp;
         }
     }
 }

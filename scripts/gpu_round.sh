@@ -1,0 +1,21 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench (both arms), ncu launch list, ncu full captures of the hot kernels.
+# Usage (from the repo root, under gpurun):  bash scripts/gpu_round.sh <tag>
+tag=${1:-r1}
+out=gpurun_out
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/${tag}_smi.csv
+python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $out/${tag}_pytest_gpu.log
+tail -3 $out/${tag}_pytest_gpu.log
+python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_ref.json 2>> $out/${tag}_bench.err
+B="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+$B > $out/${tag}_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv $B > $out/${tag}_ncu_launch.log 2>&1
+P="python scratch/tc_prof.py 18944 predict"
+$P > $out/${tag}_plain_p.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_tc_gram -s 1 -c 1 -f -o $out/${tag}_predict $P > $out/${tag}_ncu_p.log 2>&1
+T="python scratch/tc_prof.py 18944 train"
+$T > $out/${tag}_plain_t.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'k_tc_gram|k_tc_grad|k_reduce' -s 3 -c 3 -f -o $out/${tag}_train $T > $out/${tag}_ncu_t.log 2>&1
+cat $out/${tag}_bench.json
