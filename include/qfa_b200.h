@@ -176,6 +176,13 @@ int qfa_prepare_batch(const float* flux, const float* zqso, const float* wav, co
 int qfa_selftest_umma(const float* A, const float* Bimg_hi, const float* Bimg_lo, float* D, int split,
                       int* err_flag, void* stream);
 
+/*
+ * Debug/profiling aid: `device_buffer` (long long[nkb * 16 * 4], or NULL to switch off) receives clock64 stamps of
+ * the first tile of CTA 0 of every following k_tc_gram launch: per K-block and warp {enter, stage free, operands
+ * written, done}.  Not part of the reference-facing surface.
+ */
+int qfa_debug_set_trace(void* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,10 @@ static int cuda_fail(cudaError_t e, const char* what) {
     } while (0)
 
 extern "C" int qfa_abi_version(void) { return QFA_ABI_VERSION; }
+
+// debug: device buffer that k_tc_gram fills with clock64 stamps of CTA 0's first tile (see TcGramArgs::trace)
+static long long* g_trace = nullptr;
+extern "C" int qfa_debug_set_trace(void* device_buffer) { g_trace = (long long*)device_buffer; return 0; }
 extern "C" const char* qfa_last_error_string(void) { return g_err; }
 
 // ---------------------------------------------------------------------------------------
@@ -130,17 +134,19 @@ static inline bool tc_use(int Nh, int precision, int B, int flags) {
 }
 
 // Tile heights: the tile count should be a whole number of waves of num_sms() persistent CTAs.  Heights are
-// multiples of `quantum` (16: rows are dealt round-robin to the 16 warps of a CTA; 32 for the train path, whose
-// gradient kernel walks the tiles in 32-spectra chunks); n_hi tiles are one quantum taller than the others.
+// multiples of 8 (a worker warp of k_tc_gram owns 8 consecutive rows), at most tcg::TSH = 120 (15 worker warps);
+// n_hi tiles are 8 rows taller than the others.
 static tcg::TileSched tile_sched(int B, int quantum, int* ntiles) {
     tcg::TileSched ts;
     const long nsm = num_sms();
-    if (B <= 0) { ts.r_hi = ts.r_lo = tcg::TS; ts.n_hi = 0; *ntiles = 0; return ts; }
-    const long waves = ((long)B + nsm * tcg::TS - 1) / (nsm * tcg::TS);
+    const long H = tcg::TSH;
+    if (B <= 0) { ts.r_hi = ts.r_lo = (int)H; ts.n_hi = 0; *ntiles = 0; return ts; }
+    const long waves = ((long)B + nsm * H - 1) / (nsm * H);
     const long slots = nsm * waves;
     long r_lo = (B / slots) / quantum * quantum;
     if (r_lo < quantum) r_lo = quantum;
-    long r_hi = r_lo + quantum > tcg::TS ? tcg::TS : r_lo + quantum;
+    if (r_lo > H) r_lo = H;
+    long r_hi = r_lo + quantum > H ? H : r_lo + quantum;
     long rest = (long)B - slots * r_lo;
     long n_hi = (rest > 0 && r_hi > r_lo) ? (rest + (r_hi - r_lo) - 1) / (r_hi - r_lo) : 0;
     if (n_hi > slots) n_hi = slots;
@@ -156,7 +162,7 @@ static TcPlan plan_tc(int Nb, int Nr, int B, bool want_qa, int quantum = 1) {
     const int P = Nb + Nr;
     p.nkb = (P + tcg::KB - 1) / tcg::KB;
     p.npt = (P + tcg::PT - 1) / tcg::PT;
-    p.ts = tile_sched(B, quantum < 16 ? 16 : quantum, &p.ntiles);
+    p.ts = tile_sched(B, quantum < 8 ? 8 : quantum, &p.ntiles);
     size_t o = 0;
     p.off_pb = o; o = align_up(o + (size_t)p.nkb * tcg::PB_TILE, 1024);
     p.off_qa = o; if (want_qa) o = align_up(o + (size_t)p.npt * tcg::QA_TILE, 1024);
@@ -171,7 +177,7 @@ struct TcTrainPlan {
 static TcTrainPlan plan_tc_train(int Nb, int Nr, int Nh, int B) {
     TcTrainPlan p;
     const int P = Nb + Nr;
-    p.t = plan_tc(Nb, Nr, B, true, tcg::GC);
+    p.t = plan_tc(Nb, Nr, B, true, 8);
     p.nchunks = p.t.ntiles * 4;
     int ns = num_sms() / p.t.npt;
     if (ns > p.nchunks) ns = p.nchunks;
@@ -344,7 +350,7 @@ static int train_accumulate_tc(const QfaModel* m, const float* delta, const floa
     TcGramArgs a;
     a.f = f; a.B = B; a.ts = pl.t.ts; a.ntiles = pl.t.ntiles; a.nkb = pl.t.nkb; a.npt = pl.t.npt;
     a.PB = PB; a.QA = QA; a.nll = nll_out; a.hmean = nullptr; a.hcov = nullptr; a.cont = nullptr; a.unc = nullptr;
-    a.sm_b2 = sm_b2; a.sm_kc = sm_kc; a.hasblue = nullptr; a.tile_sums = tsums;
+    a.sm_b2 = sm_b2; a.sm_kc = sm_kc; a.hasblue = nullptr; a.tile_sums = tsums; a.trace = g_trace;
     int grid = pl.t.ntiles < num_sms() ? pl.t.ntiles : num_sms();
     k_tc_gram<TC_TRAIN><<<grid, NTHREADS, Cfg<TC_TRAIN>::SMEM_BYTES, st>>>(a);
     CK(cudaGetLastError());
@@ -352,7 +358,7 @@ static int train_accumulate_tc(const QfaModel* m, const float* delta, const floa
     ga.f = f; ga.B = B; ga.ts = pl.t.ts; ga.nchunks = pl.nchunks; ga.nsplit = pl.nsplit; ga.QA = QA; ga.sm_b2 = sm_b2; ga.sm_kc = sm_kc;
     ga.zero = reinterpret_cast<const uint8_t*>(PB) + sw128_offset_host(36, 0);
     ga.part = part; ga.spart = spart; ga.accumulate = 0;
-    k_tc_grad<<<dim3(pl.t.npt, pl.nsplit), NTHREADS, GradSmem::BYTES, st>>>(ga);
+    k_tc_grad<<<dim3(pl.t.npt, pl.nsplit), GRAD_THREADS, GradSmem::BYTES, st>>>(ga);
     CK(cudaGetLastError());
     ReduceArgs<float> ra;
     ra.part = part; ra.spart = spart; ra.nll = tsums; ra.hasblue = tsums + 1; ra.scal = f.scal;   // pre-folded per 32 rows
@@ -427,7 +433,7 @@ static int predict_tc(const QfaModel* m, const float* flux, const float* error, 
     a.f = make_field<float>(m, flux, error, zabs, mask);
     a.B = B; a.ts = pl.ts; a.ntiles = pl.ntiles; a.nkb = pl.nkb; a.npt = pl.npt;
     a.PB = PB; a.QA = QA; a.nll = nll; a.hmean = hmean; a.hcov = hcov; a.cont = cont; a.unc = unc;
-    a.sm_b2 = nullptr; a.sm_kc = nullptr; a.hasblue = nullptr; a.tile_sums = nullptr;
+    a.sm_b2 = nullptr; a.sm_kc = nullptr; a.hasblue = nullptr; a.tile_sums = nullptr; a.trace = g_trace;
     int grid = pl.ntiles < num_sms() ? pl.ntiles : num_sms();
     k_tc_gram<TC_PREDICT><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(a);
     CK(cudaGetLastError());
