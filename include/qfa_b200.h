@@ -182,6 +182,8 @@ int qfa_selftest_umma(const float* A, const float* Bimg_hi, const float* Bimg_lo
  * written, done}.  Not part of the reference-facing surface.
  */
 int qfa_debug_set_trace(void* device_buffer);
+/* same for k_tc_grad: CTA (0,0), long long[nchunks_of_that_cta * 16 * 8]: per chunk and warp 8 stamps */
+int qfa_debug_set_trace_grad(void* device_buffer);
 
 #ifdef __cplusplus
 }

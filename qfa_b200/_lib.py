@@ -80,6 +80,7 @@ SIGNATURES = {
     "qfa_prepare_batch": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP]),
     "qfa_selftest_umma": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP]),
     "qfa_debug_set_trace": (_I, [_VP]),
+    "qfa_debug_set_trace_grad": (_I, [_VP]),
 }
 
 

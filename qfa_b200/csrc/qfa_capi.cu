@@ -40,7 +40,9 @@ extern "C" int qfa_abi_version(void) { return QFA_ABI_VERSION; }
 
 // debug: device buffer that k_tc_gram fills with clock64 stamps of CTA 0's first tile (see TcGramArgs::trace)
 static long long* g_trace = nullptr;
+static long long* g_trace_grad = nullptr;
 extern "C" int qfa_debug_set_trace(void* device_buffer) { g_trace = (long long*)device_buffer; return 0; }
+extern "C" int qfa_debug_set_trace_grad(void* device_buffer) { g_trace_grad = (long long*)device_buffer; return 0; }
 extern "C" const char* qfa_last_error_string(void) { return g_err; }
 
 // ---------------------------------------------------------------------------------------
@@ -171,7 +173,8 @@ static TcPlan plan_tc(int Nb, int Nr, int B, bool want_qa, int quantum = 1) {
 }
 struct TcTrainPlan {
     TcPlan t;
-    int nchunks, nsplit, ntiles_blue;
+    int nchunks, nsplit, ntiles_blue;      // nsplit = max(ns_blue, ns_red): number of partial buffers
+    int ns_blue, ns_red;
     size_t off_b2, off_kc, off_tsums, off_part, off_spart, total;
 };
 static TcTrainPlan plan_tc_train(int Nb, int Nr, int Nh, int B) {
@@ -179,11 +182,28 @@ static TcTrainPlan plan_tc_train(int Nb, int Nr, int Nh, int B) {
     const int P = Nb + Nr;
     p.t = plan_tc(Nb, Nr, B, true, 8);
     p.nchunks = p.t.ntiles * 4;
-    int ns = num_sms() / p.t.npt;
-    if (ns > p.nchunks) ns = p.nchunks;
-    if (ns < 1) ns = 1;
-    p.nsplit = ns;
     p.ntiles_blue = (Nb + tcg::PT - 1) / tcg::PT;
+    if (p.ntiles_blue > p.t.npt) p.ntiles_blue = p.t.npt;
+    {
+        // k_tc_grad runs ONE wave of CTAs; a pixel tile with blue pixels costs `ratio` times a red one per spectrum
+        // (QFA_GRAD_BLUE_COST, default 1.8).  Pick the CTAs per tile that minimise the slowest CTA.
+        static double ratio = -1.0;
+        if (ratio < 0) { const char* e = getenv("QFA_GRAD_BLUE_COST"); ratio = e ? atof(e) : 1.8; if (ratio < 1.0) ratio = 1.0; }
+        const int ntb = p.ntiles_blue, ntr = p.t.npt - ntb, nsm = num_sms();
+        int best_b = 1, best_r = 1; double best = 1e30;
+        for (int r = 1; r <= nsm; ++r) {
+            int b = ntb > 0 ? (nsm - ntr * r) / ntb : 1;
+            if (ntr == 0) { b = nsm / (ntb > 0 ? ntb : 1); }
+            if (b < 1) break;
+            const double t = (ntb > 0 ? ratio / b : 0.0) > (ntr > 0 ? 1.0 / r : 0.0) ? ratio / b : 1.0 / r;
+            if (t < best) { best = t; best_b = b; best_r = r; }
+            if (ntr == 0) break;
+        }
+        if (best_b > p.nchunks) best_b = p.nchunks > 0 ? p.nchunks : 1;
+        if (best_r > p.nchunks) best_r = p.nchunks > 0 ? p.nchunks : 1;
+        p.ns_blue = best_b; p.ns_red = best_r;
+        p.nsplit = best_b > best_r ? best_b : best_r;
+    }
     size_t o = p.t.total;
     o = align_up(o, 1024);
     p.off_b2 = o;      o = align_up(o + (size_t)p.t.ntiles * tcg::B2_TILE, 1024);
@@ -313,7 +333,7 @@ static int train_accumulate_t(const QfaModel* m, const float* delta, const float
     ReduceArgs<T> ra;
     ra.part = part; ra.spart = spart; ra.nll = nll; ra.hasblue = hasblue; ra.scal = make_field<T>(m, 0, 0, 0, 0).scal;
     ra.acc = acc; ra.P = P; ra.Nb = Nb; ra.Nh = Nh; ra.B = B; ra.stride = 1; ra.nsp = (double)B; ra.nsplit = nsplit_used;
-    ra.ntiles_blue = pl.ntiles_blue; ra.ntiles = pl.ntiles;
+    ra.ntiles_blue = pl.ntiles_blue; ra.ntiles = pl.ntiles; ra.nsplit_red = nsplit_used; ra.tile_px = 128;
     size_t n_el = part_len(P, Nb, Nh);
     int blocks = (int)((n_el + 255) / 256);
     k_reduce<T><<<blocks, 256, 0, st>>>(ra);
@@ -355,15 +375,17 @@ static int train_accumulate_tc(const QfaModel* m, const float* delta, const floa
     k_tc_gram<TC_TRAIN><<<grid, NTHREADS, Cfg<TC_TRAIN>::SMEM_BYTES, st>>>(a);
     CK(cudaGetLastError());
     TcGradArgs ga;
-    ga.f = f; ga.B = B; ga.ts = pl.t.ts; ga.nchunks = pl.nchunks; ga.nsplit = pl.nsplit; ga.QA = QA; ga.sm_b2 = sm_b2; ga.sm_kc = sm_kc;
+    ga.f = f; ga.B = B; ga.ts = pl.t.ts; ga.nchunks = pl.nchunks; ga.ns_blue = pl.ns_blue; ga.ns_red = pl.ns_red;
+    ga.ntiles_blue = pl.ntiles_blue; ga.npt = pl.t.npt; ga.QA = QA; ga.sm_b2 = sm_b2; ga.sm_kc = sm_kc;
     ga.zero = reinterpret_cast<const uint8_t*>(PB) + sw128_offset_host(36, 0);
-    ga.part = part; ga.spart = spart; ga.accumulate = 0;
-    k_tc_grad<<<dim3(pl.t.npt, pl.nsplit), GRAD_THREADS, GradSmem::BYTES, st>>>(ga);
+    ga.part = part; ga.spart = spart; ga.accumulate = 0; ga.trace = g_trace_grad;
+    const int grad_ctas = pl.ntiles_blue * pl.ns_blue + (pl.t.npt - pl.ntiles_blue) * pl.ns_red;
+    k_tc_grad<<<grad_ctas, GRAD_THREADS, GradSmem::BYTES, st>>>(ga);
     CK(cudaGetLastError());
     ReduceArgs<float> ra;
     ra.part = part; ra.spart = spart; ra.nll = tsums; ra.hasblue = tsums + 1; ra.scal = f.scal;   // pre-folded per 32 rows
     ra.acc = acc; ra.P = P; ra.Nb = Nb; ra.Nh = Nh; ra.B = pl.t.ntiles * 4; ra.stride = 2; ra.nsp = (double)B;
-    ra.nsplit = pl.nsplit; ra.ntiles_blue = pl.ntiles_blue; ra.ntiles = pl.t.npt;
+    ra.nsplit = pl.ns_blue; ra.nsplit_red = pl.ns_red; ra.tile_px = PT; ra.ntiles_blue = pl.ntiles_blue; ra.ntiles = pl.t.npt;
     size_t n_pl = part_len(P, Nb, Nh);
     k_reduce<float><<<(int)((n_pl + 255) / 256), 256, 0, st>>>(ra);
     CK(cudaGetLastError());

@@ -484,6 +484,7 @@ struct ReduceArgs {
     T* acc;
     int P, Nb, Nh, B, nsplit, ntiles_blue, ntiles;   // B = length of nll / hasblue (per spectrum, or pre-folded partial sums)
     int stride;                                       // element stride of nll / hasblue
+    int nsplit_red, tile_px;                          // pixels of tiles >= ntiles_blue have nsplit_red partials (tile_px pixels per tile)
     double nsp;                                       // number of spectra these sums stand for
 };
 
@@ -501,8 +502,16 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs<T> r) {
         if (gid < PH + r.P + r.Nb) { pi = gid; ai = gid; }                         // F, Psi, omega
         else if (gid < PH + 2 * (size_t)r.P + r.Nb) { pi = gid; ai = o_cnt + (gid - (PH + r.P + r.Nb)); }
         else { pi = gid; ai = o_dmu + (gid - (PH + 2 * (size_t)r.P + r.Nb)); }
+        // pixel this element belongs to -> how many partials exist for it
+        size_t px;
+        if (gid < PH) px = gid / r.Nh;
+        else if (gid < PH + r.P) px = gid - PH;
+        else if (gid < PH + r.P + r.Nb) px = gid - PH - r.P;
+        else if (gid < PH + 2 * (size_t)r.P + r.Nb) px = gid - (PH + r.P + r.Nb);
+        else px = gid - (PH + 2 * (size_t)r.P + r.Nb);
+        const int ns = ((int)(px / r.tile_px) < r.ntiles_blue) ? r.nsplit : r.nsplit_red;
         T s = T(0);
-        for (int k = 0; k < r.nsplit; ++k) s += r.part[(size_t)k * plen + pi];
+        for (int k = 0; k < ns; ++k) s += r.part[(size_t)k * plen + pi];
         r.acc[ai] += s;
     }
     if (blockIdx.x == gridDim.x - 1) {

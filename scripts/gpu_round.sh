@@ -11,11 +11,11 @@ python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench r
 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_ref.json 2>> $out/${tag}_bench.err
 B="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
 $B > $out/${tag}_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv $B > $out/${tag}_ncu_launch.log 2>&1
-P="python scratch/tc_prof.py 18944 predict"
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_tc|k_gram|k_grad|k_reduce|k_adam|k_final|k_clip|k_smooth|k_prepare' -c 400 --csv --log-file $out/${tag}_launches.csv $B > $out/${tag}_ncu_launch.log 2>&1
+P="python scratch/tc_prof.py 17760 predict"
 $P > $out/${tag}_plain_p.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_tc_gram -s 1 -c 1 -f -o $out/${tag}_predict $P > $out/${tag}_ncu_p.log 2>&1
-T="python scratch/tc_prof.py 18944 train"
+T="python scratch/tc_prof.py 17760 train"
 $T > $out/${tag}_plain_t.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'k_tc_gram|k_tc_grad|k_reduce' -s 3 -c 3 -f -o $out/${tag}_train $T > $out/${tag}_ncu_t.log 2>&1
 cat $out/${tag}_bench.json
