@@ -51,7 +51,7 @@ def parse():
 WORKLOADS = {
     # name: (grid, Nh, kind, default spectra per GPU, cpu sample)
     "sdss100k_predict": ("sdss", 8, "predict", 100_000, 192),
-    "sdss_train": ("sdss", 8, "train", 75_776, 64),        # 148 SMs x 4 waves x 128-spectra tiles
+    "sdss_train": ("sdss", 8, "train", 71_040, 64),        # 148 SMs x 4 waves x 120-spectra tiles
     "l32_train": ("l32", 32, "train", 65_536, 256),
     "desi_score": ("desi", 8, "score", 32_768, 4),
 }

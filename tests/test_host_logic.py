@@ -137,3 +137,72 @@ def test_synthetic_loader_protocol_and_sharding():
     allrows = torch.cat(seen)
     assert allrows.shape[0] == 40
     assert torch.equal(torch.sort(allrows[:, 0])[0], torch.sort(data["delta"][:, 0])[0])
+
+
+# ----------------------------------------------------------------------------- data parallel host logic (gloo, 2 ranks)
+def _pack_acc(model, extra, nsp):
+    """oracle sums / counts -> the library's `acc` layout (include/qfa_b200.h)."""
+    s, c = extra["sums"], extra["counts"]
+    parts = [np.asarray(s["F"]).ravel(), np.asarray(s["Psi"]), np.asarray(s["omega"]),
+             np.array([s["tau0"], s["c0"], s["beta"]]), np.asarray(c["Psi"]),
+             np.array([c["tau0"], c["c0"], c["beta"]], dtype=np.float64),
+             np.array([extra["nll"].sum(), float(nsp)]), np.asarray(extra["dmu"])]
+    acc = torch.tensor(np.concatenate([np.asarray(p, np.float64).ravel() for p in parts]))
+    assert acc.numel() == model.Nparams + model.Npix + 3 + 2 + model.Npix
+    return acc
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from oracle import qfa_lowrank          # checker only
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        grid = synth.GridSpec("t", 1150.0, 6e-4, 96)
+        P, mu = synth.smooth_random_params(grid, 4, seed=1)
+        data = synth.make_spectra(P, mu, grid, 24, seed=2)
+        data["mask"][:, 5] = False                       # a pixel masked everywhere: 0/0 -> NaN on every rank alike
+        Pn = {k: np.asarray(v) for k, v in P.items()}
+        m = QFA(grid.Nb, grid.Nr, 4, cpu, model_params=Pn)
+        m.enable_data_parallel()
+        assert m._dp
+        ld = synth.SyntheticLoader(data, mu, batch_size=24, rank=rank, world=world, seed=3, shuffle=False)
+        ld.rewind()
+        d, e, z, k = ld.next_batch()                     # this rank's half of the global batch
+        assert d.shape[0] == 12 and not ld.have_next_batch()
+        _, _, ex = qfa_lowrank.forward(Pn, d.numpy(), e.numpy(), z.numpy(), k.numpy(), grid.Nb, return_sums=True)
+        acc = _pack_acc(m, ex, d.shape[0])
+        m._allreduce(acc)                                # the ONE collective of a train step
+        n = m.Nparams
+        with np.errstate(divide="ignore", invalid="ignore"):
+            a = acc.numpy()
+            gF = a[:m.Npix * m.Nh].reshape(m.Npix, m.Nh) / a[n:n + m.Npix, None]     # divide AFTER the reduce
+            gt0 = a[n - 3] / a[n + m.Npix]
+        loss = float(m._loss_from_acc(acc))
+        _, gref, _ = qfa_lowrank.forward(Pn, data["delta"].numpy(), data["error"].numpy(), data["zabs"].numpy(),
+                                         data["mask"].numpy(), grid.Nb, return_sums=True)
+        lref, _ = qfa_lowrank.forward(Pn, data["delta"].numpy(), data["error"].numpy(), data["zabs"].numpy(),
+                                      data["mask"].numpy(), grid.Nb)
+        q.put((rank, relerr(gF, gref["F"]), abs(gt0 - gref["tau0"]) / abs(gref["tau0"]), abs(loss - lref) / abs(lref),
+               float(a[n + m.Npix + 4])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_allreduce_gloo_world2():
+    """N>1 host path on CPU: shard by rank, all-reduce the packed sums/counts over gloo, divide after the
+    reduce (quirk Q4) == single-process result on the global batch."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, eF, et0, el, nsp in res:
+        assert eF < 1e-12 and et0 < 1e-12 and el < 1e-12, (rank, eF, et0, el)
+        assert nsp == 24.0
