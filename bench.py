@@ -57,6 +57,16 @@ WORKLOADS = {
 }
 
 
+def measured_traffic(kind, grid_name, Nh, nspec):
+    """DRAM bytes per launch of the dominant kernel, scaled from the committed `ncu --set full` capture
+    (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per spectrum of that capture)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        return t[f"{kind}_{grid_name}_nh{Nh}"]["dram_bytes_per_spectrum"] * nspec
+    except Exception:
+        return None
+
+
 def bytes_per_spectrum(kind, P, Nb, Nh):
     """Algorithmic HBM bytes per spectrum."""
     if kind == "predict":
@@ -83,43 +93,52 @@ def model_and_params(grid_name, Nh):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region.  The timed region of the default run is ~10 ms, far
+    shorter than nvidia-smi's sampling period, so NVML is polled directly from a thread (every ~1 ms)."""
 
     def __init__(self, index):
-        self.rows, self.p = [], None
+        self.rows, self.ok, self.stop_flag = [], False, False
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:
-            self.p = None
+            self.ok = False
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append((time.time(), line.strip()))
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.rows.append((time.time(), sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def stop(self, t0, t1):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows[-3:]]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
-            try:
-                sm.append(float(f[0])); mx = float(f[1])
-            except Exception:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.t.join(timeout=1.0)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        if not rows:                                   # region shorter than one poll: nearest samples around it
+            rows = sorted(self.rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))[:3]
+        sm = [r[1] for r in rows]
+        reasons = sorted(n for n, bit in names.items() if any(r[2] & bit for r in rows))
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
                 "samples": len(sm)}
 
 
@@ -268,7 +287,8 @@ def measure_workload(name, args, rank, world, peaks, want_e2e, want_cpu, nspec_o
     achieved = nspec * args.steps * bps / (ms * 1e-3) / 1e9        # per GPU, GB/s of algorithmic bytes
     res.update(value=value, ms_per_step=ms / args.steps, clocks=clocks, gpu_launches=launches_per_step * args.steps,
                roofline={"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": measured_traffic(kind, grid_name, Nh, nspec),
                          "kernel": kernel_name,
                          "bytes_per_spectrum": bps, "peak_source": peaks["source"]},
                config={"workload": name, "kind": kind, "grid": grid_name, "Npix": grid.Npix, "Nb": grid.Nb, "Nh": Nh,

@@ -181,14 +181,14 @@ static TcTrainPlan plan_tc_train(int Nb, int Nr, int Nh, int B) {
     TcTrainPlan p;
     const int P = Nb + Nr;
     p.t = plan_tc(Nb, Nr, B, true, 8);
-    p.nchunks = p.t.ntiles * 4;
+    p.nchunks = p.t.ntiles * tcg::GCT;
     p.ntiles_blue = (Nb + tcg::PT - 1) / tcg::PT;
     if (p.ntiles_blue > p.t.npt) p.ntiles_blue = p.t.npt;
     {
         // k_tc_grad runs ONE wave of CTAs; a pixel tile with blue pixels costs `ratio` times a red one per spectrum
-        // (QFA_GRAD_BLUE_COST, default 1.2: measured, the kernel is latency- not MUFU-bound).  Pick the CTAs per tile that minimise the slowest CTA.
+        // (QFA_GRAD_BLUE_COST, default 1.5, measured).  Pick the CTAs per tile that minimise the slowest CTA.
         static double ratio = -1.0;
-        if (ratio < 0) { const char* e = getenv("QFA_GRAD_BLUE_COST"); ratio = e ? atof(e) : 1.2; if (ratio < 1.0) ratio = 1.0; }
+        if (ratio < 0) { const char* e = getenv("QFA_GRAD_BLUE_COST"); ratio = e ? atof(e) : 1.5; if (ratio < 1.0) ratio = 1.0; }
         const int ntb = p.ntiles_blue, ntr = p.t.npt - ntb, nsm = num_sms();
         int best_b = 1, best_r = 1; double best = 1e30;
         for (int r = 1; r <= nsm; ++r) {
