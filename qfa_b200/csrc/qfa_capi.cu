@@ -11,6 +11,7 @@
 #include "qfa_tc_selftest.cuh"
 #include "qfa_tc_gram.cuh"
 #include "qfa_tc_grad.cuh"
+#include "qfa_tc_gram32.cuh"
 
 using namespace qfa;
 
@@ -215,11 +216,46 @@ static TcTrainPlan plan_tc_train(int Nb, int Nr, int Nh, int B) {
     return p;
 }
 
+// ---- tensor-core Grams for 16 < Nh <= 32 (QFA_PREC_TF32): k_tc_gram32 + k_solve32, then the float k_grad
+struct Tc32Plan {
+    int nkb, ntiles, npix_tiles, nsplit, ntiles_blue;
+    tcg::TileSched ts;
+    size_t off_pb, off_gram, off_small, off_hasblue, off_nll, off_part, off_spart, total;
+};
+static inline bool tc32_eligible(int Nh, int precision) { return precision == QFA_PREC_TF32 && Nh > 16 && Nh <= 32; }
+static Tc32Plan plan_tc32(int Nb, int Nr, int Nh, int B) {
+    Tc32Plan p;
+    const int P = Nb + Nr;
+    p.nkb = (P + tcg::KB - 1) / tcg::KB;
+    p.ts = tile_sched(B, 8, &p.ntiles);
+    p.npix_tiles = (P + 127) / 128;
+    p.ntiles_blue = (Nb + 127) / 128;
+    int want = (4 * num_sms() + p.npix_tiles - 1) / p.npix_tiles;
+    if (want > B) want = B;
+    if (want < 1) want = 1;
+    p.nsplit = want;
+    const size_t Bn = B > 0 ? B : 1;
+    size_t o = 0;
+    p.off_pb = o;      o = align_up(o + (size_t)p.nkb * tcg32::PB32_KB_BYTES + 16, 1024);
+    p.off_gram = o;    o = align_up(o + Bn * tcg32::G32_STRIDE * 4, 256);
+    p.off_small = o;   o = align_up(o + Bn * SmallLayout<32>::len * 4, 256);
+    p.off_hasblue = o; o = align_up(o + Bn * 4, 256);
+    p.off_nll = o;     o = align_up(o + Bn * 4, 256);
+    p.off_part = o;    o = align_up(o + (size_t)p.nsplit * part_len(P, Nb, Nh) * 4, 256);
+    p.off_spart = o;   o = align_up(o + (size_t)p.nsplit * p.npix_tiles * 3 * 4, 256);
+    p.total = o;
+    return p;
+}
+
 extern "C" size_t qfa_train_workspace_bytes(int Nb, int Nr, int Nh, int B, int precision) {
     if (Nb < 0 || Nr < 0 || Nb + Nr <= 0 || Nh < 1 || Nh > 32 || B < 0) return 0;
     size_t cc = plan_train(Nb, Nr, Nh, B, precision).total;
     if (tc_eligible(Nh, precision)) {
         size_t tc = plan_tc_train(Nb, Nr, Nh, B).total;
+        return tc > cc ? tc : cc;
+    }
+    if (tc32_eligible(Nh, precision)) {
+        size_t tc = plan_tc32(Nb, Nr, Nh, B).total;
         return tc > cc ? tc : cc;
     }
     return cc;
@@ -392,6 +428,54 @@ static int train_accumulate_tc(const QfaModel* m, const float* delta, const floa
     return 0;
 }
 
+static int train_accumulate_tc32(const QfaModel* m, const float* delta, const float* error, const float* zabs,
+                                 const uint8_t* mask, int B, char* ws, const Tc32Plan& pl, float* acc, float* nll_out,
+                                 int flags, cudaStream_t st) {
+    using namespace tcg32;
+    const int P = m->Nb + m->Nr, Nb = m->Nb, Nh = m->Nh;
+    if (flags & QFA_FLAG_ZERO_ACC) CK(cudaMemsetAsync(acc, 0, qfa_acc_len(m->Nb, m->Nr, Nh) * sizeof(float), st));
+    if (B == 0) return 0;
+    float* PB = reinterpret_cast<float*>(ws + pl.off_pb);
+    float* gram = reinterpret_cast<float*>(ws + pl.off_gram);
+    float* small = reinterpret_cast<float*>(ws + pl.off_small);
+    float* hasblue = reinterpret_cast<float*>(ws + pl.off_hasblue);
+    float* nll = nll_out ? nll_out : reinterpret_cast<float*>(ws + pl.off_nll);
+    float* part = reinterpret_cast<float*>(ws + pl.off_part);
+    float* spart = reinterpret_cast<float*>(ws + pl.off_spart);
+    const size_t n_el = (size_t)pl.nkb * PB32_ROWS * tcg::KB;
+    int blocks = (int)((n_el + 255) / 256);
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    k_tc_build_images32<<<blocks, 256, 0, st>>>(m->params, P, Nh, PB, pl.nkb);
+    CK(cudaGetLastError());
+    static bool attr_done = false;
+    if (!attr_done) {
+        CK(cudaFuncSetAttribute(k_tc_gram32, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM32_BYTES));
+        CK(cudaFuncSetAttribute(k_solve32, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE32_SMEM));
+        attr_done = true;
+    }
+    Field<float> f = make_field<float>(m, delta, error, zabs, mask);
+    TcGram32Args a;
+    a.f = f; a.B = B; a.ts = pl.ts; a.ntiles = pl.ntiles; a.nkb = pl.nkb; a.PB = PB; a.gram = gram;
+    int grid = pl.ntiles < num_sms() ? pl.ntiles : num_sms();
+    k_tc_gram32<<<grid, tcg::NTHREADS, SMEM32_BYTES, st>>>(a);
+    CK(cudaGetLastError());
+    int sblocks = (B + SOLVE32_WARPS - 1) / SOLVE32_WARPS;
+    if (sblocks > 2 * num_sms()) sblocks = 2 * num_sms();
+    k_solve32<<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, small, nll, hasblue);
+    CK(cudaGetLastError());
+    GradArgs<float> gr;
+    gr.f = f; gr.B = B; gr.nsplit = pl.nsplit; gr.small = small; gr.part = part; gr.spart = spart; gr.accumulate = 0;
+    CK(dispatch_grad<float>(32, gr, pl.npix_tiles, st));
+    ReduceArgs<float> ra;
+    ra.part = part; ra.spart = spart; ra.nll = nll; ra.hasblue = hasblue; ra.scal = f.scal;
+    ra.acc = acc; ra.P = P; ra.Nb = Nb; ra.Nh = Nh; ra.B = B; ra.stride = 1; ra.nsp = (double)B; ra.nsplit = pl.nsplit;
+    ra.ntiles_blue = pl.ntiles_blue; ra.ntiles = pl.npix_tiles; ra.nsplit_red = pl.nsplit; ra.tile_px = 128;
+    size_t n_pl = part_len(P, Nb, Nh);
+    k_reduce<float><<<(int)((n_pl + 255) / 256), 256, 0, st>>>(ra);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int qfa_train_accumulate(const QfaModel* model, const float* delta, const float* error,
                                     const float* zabs, const uint8_t* mask, int B, void* workspace,
                                     size_t workspace_bytes, void* acc, void* nll_per_spectrum, int precision,
@@ -413,6 +497,13 @@ extern "C" int qfa_train_accumulate(const QfaModel* model, const float* delta, c
             return fail(QFA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", tp.total, workspace_bytes);
         return train_accumulate_tc(model, delta, error, zabs, mask, B, (char*)workspace, tp, (float*)acc,
                                    (float*)nll_per_spectrum, flags, st);
+    }
+    if (tc32_eligible(model->Nh, precision) && (B >= tc_min_batch() || (flags & QFA_FLAG_FORCE_TENSOR))) {
+        Tc32Plan tp = plan_tc32(model->Nb, model->Nr, model->Nh, B);
+        if (B > 0 && workspace_bytes < tp.total)
+            return fail(QFA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", tp.total, workspace_bytes);
+        return train_accumulate_tc32(model, delta, error, zabs, mask, B, (char*)workspace, tp, (float*)acc,
+                                     (float*)nll_per_spectrum, flags, st);
     }
     if (precision == QFA_PREC_FP64)
         return train_accumulate_t<double>(model, delta, error, zabs, mask, B, (char*)workspace, pl, (double*)acc,

@@ -1,0 +1,390 @@
+// Tensor-core (tcgen05 / TMEM) masked weighted Grams for 8 < Nh <= 32 (train step), sm_100a.
+//
+//   k_tc_gram32   persistent, one CTA per SM, tile = up to 120 spectra x all pixels, same worker / control-warp
+//                 organisation and the same generated-operand pipeline as k_tc_gram<TRAIN> (qfa_tc_gram.cuh):
+//                    D[b,(k,l)] = sum_i s2[b,i] (F_ik F_il)   -> M - I      (model.py:126-132, utils.py:29-32)
+//                    D[b,(k,l)] = sum_i s3[b,i] (F_ik F_il)   -> M2         (quirk Q2 of model.py:137)
+//                    D[b,k]     = sum_i wb[b,i] F_ik , sum_i wb2[b,i] F_ik  -> b, b2
+//                 With Nh = 32 the Khatri-Rao image has 528 columns per operand: 2 x 528 + 64 accumulator columns do not
+//                 fit the 512 TMEM columns, so the columns are covered in THREE passes over the tile (224 + 224 + 80 columns
+//                 for each of M and M2; b / b2 ride in pass 0).  The operands are re-generated in every pass (the tile's
+//                 inputs are re-read, mostly from L2); after each pass the accumulators are drained to a per-spectrum
+//                 scratch row in global memory.
+//   k_solve32     one warp per spectrum: scratch row -> Cholesky / inverse / K = M^-1 M2 / c in shared memory (double),
+//                 NLL, and the hand-off record that the pixel-major gradient kernel k_grad<float,32> reads.
+#pragma once
+#include "qfa_tc_gram.cuh"
+#include "qfa_kernels.cuh"
+
+namespace qfa {
+namespace tcg32 {
+
+using namespace tc;
+using namespace tcg;
+
+constexpr int H32 = 32;
+constexpr int NP2_32 = H32 * (H32 + 1) / 2;        // 528 Khatri-Rao columns (k <= l)
+constexpr int PB32_ROWS = NP2_32 + H32;            // 560 image rows per K-block: 528 products, then F
+constexpr int PB32_KB_BYTES = PB32_ROWS * 128;     // 71 680 B per K-block
+constexpr int NPASS = 3;
+constexpr int SLICE = 224;                         // Khatri-Rao columns per pass (last pass: 80)
+constexpr int NSTAGE32 = 2;
+constexpr int NPB32 = 3;
+constexpr int STAGE32_BYTES = 4 * A_TILE;          // s2 | wb | s3 | wb2
+constexpr int PB32_SLOT = (SLICE + H32) * 128;     // 32 KB: a slice of the product rows + the F rows (pass 0)
+constexpr int PB32_OFF = NSTAGE32 * STAGE32_BYTES;
+constexpr int SMEM32_BYTES = PB32_OFF + NPB32 * PB32_SLOT + 1024;
+constexpr int PB32_LEAD = NPB32 - NSTAGE32;
+// TMEM columns (all 512): M slice | M2 slice | b | b2
+constexpr int T_A = 0, T_C = SLICE, T_B = 2 * SLICE, T_D = 2 * SLICE + H32;
+// scratch row per spectrum (floats): [M - I packed (528) | M2 packed (528) | b (32) | b2 (32) | E | n_blue>0 | pad]
+constexpr int G32_M = 0, G32_M2 = NP2_32, G32_B = 2 * NP2_32, G32_B2 = 2 * NP2_32 + H32, G32_E = 2 * NP2_32 + 2 * H32;
+constexpr int G32_STRIDE = 1124;
+
+__host__ __device__ constexpr int tri32(int k, int l) { return k * H32 - k * (k - 1) / 2 + (l - k); }   // k <= l
+__host__ __device__ constexpr int slice_cols(int p) { return p < 2 ? SLICE : NP2_32 - 2 * SLICE; }
+
+// static image: PB32[kb] = 560 rows x 32 pixels (SWIZZLE_128B rows, TF32-rounded); row n < 528 -> F_ik F_il, n = tri32(k,l)
+__global__ void k_tc_build_images32(const float* __restrict__ F, int P, int Nh, float* __restrict__ PB, int nkb) {
+    const size_t n_el = (size_t)nkb * PB32_ROWS * KB;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += (size_t)gridDim.x * blockDim.x) {
+        const int kappa = (int)(e % KB), row = (int)((e / KB) % PB32_ROWS), kb = (int)(e / (KB * PB32_ROWS));
+        const int i = kb * KB + kappa;
+        float v = 0.f;
+        if (i < P) {
+            if (row < NP2_32) {
+                int k = 0, n = row;
+                while (n >= H32 - k) { n -= H32 - k; ++k; }
+                const int l = k + n;
+                if (k < Nh && l < Nh) v = __ldg(F + (size_t)i * Nh + k) * __ldg(F + (size_t)i * Nh + l);
+            } else if (row - NP2_32 < Nh) {
+                v = __ldg(F + (size_t)i * Nh + (row - NP2_32));
+            }
+        }
+        PB[(size_t)kb * (PB32_KB_BYTES / 4) + sw128_offset(row, kappa) / 4] = tf32_rna(v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 4) PB[(size_t)nkb * (PB32_KB_BYTES / 4) + threadIdx.x] = 0.f;   // 16 zero bytes (dummy mask)
+}
+
+// per-cell physics + operand generation; PASS0 also produces the wb / wb2 operands and the scalar sums
+template <int BLUE, bool PASS0>
+__device__ __forceinline__ void compute_row32(const PhysConst& pc, const PixConst& px, const RowBuf& rb, bool blue, uint32_t sa,
+                                              float& E, uint32_t& nbm, int j) {
+    const bool mk = rb.m != 0u;
+    float A = 1.0f, oz = 0.0f;
+    if (BLUE != 0) {
+        const float L2 = lg2f(1.0f + rb.z);
+        const float tau = fmaf(pc.lt0, ex2f(pc.lbe * (L2 - pc.l2zn)), pc.lC);     // utils.py:106 etc.
+        const float Ab = ex2f(-kLog2e * tau);                                       // model.py:125
+        const float powb = ex2f(pc.beta * L2);                                      // utils.py:72
+        const float root = pc.one_m_c0 - ex2f(pc.nt0l2e * powb);                    // utils.py:91
+        A = (BLUE == 1 || blue) ? Ab : 1.0f;
+        oz = px.om * (root * root);
+    }
+    const float A2 = A * A;
+    const float D = fmaf(A2, px.psi, fmaf(rb.e, rb.e, oz));                         // model.py:128-131
+    const float w = rcpf(D);
+    const float r = rb.x;
+    const float wA = w * A;
+    const float s2 = wA * A;
+    sts_f32_imm<0>(sa, mk ? tf32_round(s2) : 0.0f);
+    if (BLUE != 0) sts_f32_imm<2 * A_TILE>(sa, mk ? tf32_round(s2 * A) : 0.0f);     // s3 (= s2 on red K-blocks)
+    if (PASS0) {
+        const float wb = wA * r;
+        sts_f32_imm<A_TILE>(sa, mk ? tf32_round(wb) : 0.0f);
+        if (BLUE != 0) {
+            sts_f32_imm<3 * A_TILE>(sa, mk ? tf32_round(s2 * r) : 0.0f);            // wb2 (= wb on red K-blocks)
+            nbm |= (mk && (BLUE == 1 || blue)) ? (1u << j) : 0u;
+        }
+        const float et = fmaf(w * r, r, fmaf(kLn2, lg2f(D), kLn2Pi));               // w r^2 + ln(2 pi D)
+        E += mk ? et : 0.0f;
+    }
+}
+
+template <int BLUE, bool PASS0, int NR>
+__device__ __forceinline__ void kblock_consume32(const PhysConst& pc, const KBuf& kb, bool blue, uint32_t warp_sa, int nr,
+                                                 float (&E)[RPW], uint32_t& nbm) {
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+        if (NR > 0 ? j < NR : j < nr)
+            compute_row32<BLUE, PASS0>(pc, kb.px, kb.r[j], blue, (warp_sa ^ ((uint32_t)j << 4)) + (uint32_t)j * 128u, E[j], nbm, j);
+    }
+}
+
+struct TcGram32Args {
+    Field<float> f;
+    int B;
+    TileSched ts;
+    int ntiles, nkb;
+    const float* PB;       // [nkb][PB32_KB_BYTES/4]
+    float* gram;           // [B][G32_STRIDE]
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* ring = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar_full[NSTAGE32], bar_empty[NSTAGE32], bar_pb[NPB32], bar_gram;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float sE[TS];
+    __shared__ float sNb[TS];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const Field<float>& f = g.f;
+    const int P = f.P, Nb = f.Nb;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE32; ++s) { mbar_init(&bar_empty[s], 1); mbar_init(&bar_full[s], NWW); }
+        for (int s = 0; s < NPB32; ++s) mbar_init(&bar_pb[s], 1);
+        mbar_init(&bar_gram, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+
+    PhysConst pc;
+    {
+        const float tau0 = __ldg(f.scal + 0), c0 = __ldg(f.scal + 1);
+        pc.beta = __ldg(f.scal + 2);
+        pc.one_m_c0 = 1.0f - c0;
+        pc.nt0l2e = -tau0 * kLog2e;
+        pc.l2zn = f.llogzn * kLog2e;
+        pc.lt0 = f.lt0; pc.lbe = f.lbe; pc.lC = f.lC;
+    }
+    const int nkb = g.nkb;
+
+    uint32_t pass_iter = 0;          // counts (tile, pass) pairs of this CTA: ring / barrier parities run across passes
+    for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+        const int b0 = g.ts.first(tile);
+        const int nrows = g.B - b0 < g.ts.rows(tile) ? g.B - b0 : g.ts.rows(tile);
+        const int nr = warp < NWW ? (nrows - RPW * warp < 0 ? 0 : (nrows - RPW * warp > RPW ? RPW : nrows - RPW * warp)) : 0;
+        for (int pass = 0; pass < NPASS; ++pass, ++pass_iter) {
+            const uint32_t git0 = pass_iter * (uint32_t)nkb;
+            const int ncol = slice_cols(pass);
+            if (warp == NWW) {
+                // ----------------------------------------------------------- CONTROL warp
+                if (elect_one()) {
+                    auto issue_pb = [&](uint32_t git, int kb) {
+                        const int slot = git % NPB32;
+                        unsigned char* dst = ring + PB32_OFF + (size_t)slot * PB32_SLOT;
+                        const float* src = g.PB + (size_t)kb * (PB32_KB_BYTES / 4);
+                        const uint32_t bytes = (uint32_t)ncol * 128u + (pass == 0 ? (uint32_t)H32 * 128u : 0u);
+                        mbar_expect_tx(&bar_pb[slot], bytes);
+                        bulk_g2s(dst, src + (size_t)pass * SLICE * 32, (uint32_t)ncol * 128u, &bar_pb[slot]);
+                        if (pass == 0) bulk_g2s(dst + SLICE * 128, src + (size_t)NP2_32 * 32, H32 * 128, &bar_pb[slot]);
+                    };
+                    for (int kb = 0; kb < PB32_LEAD && kb < nkb; ++kb) issue_pb(git0 + kb, kb);
+                    const uint32_t idA = idesc_tf32(128, ncol), idB = idesc_tf32(128, H32);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        const uint32_t git = git0 + kb;
+                        const int s = git % NSTAGE32, slot = git % NPB32;
+                        const uint32_t sb = smem_u32(ring) + (uint32_t)s * (uint32_t)STAGE32_BYTES;
+                        const uint32_t pb = smem_u32(ring) + (uint32_t)PB32_OFF + (uint32_t)slot * (uint32_t)PB32_SLOT;
+                        mbar_wait_or_trap(&bar_full[s], (git / NSTAGE32) & 1);
+                        mbar_wait_or_trap(&bar_pb[slot], (git / NPB32) & 1);
+                        fence_after_sync();
+                        const bool red = kb * KB >= Nb;        // all-red K-block: s3 = s2, wb2 = wb (two operand tiles only)
+                        const uint64_t dS2 = desc_sw128_kmajor(sb), dWb = desc_sw128_kmajor(sb + A_TILE);
+                        const uint64_t dS3 = red ? dS2 : desc_sw128_kmajor(sb + 2 * A_TILE);
+                        const uint64_t dW2 = red ? dWb : desc_sw128_kmajor(sb + 3 * A_TILE);
+                        const uint64_t dP = desc_sw128_kmajor(pb), dF = desc_sw128_kmajor(pb + SLICE * 128);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t ko = (uint64_t)(2 * kk);
+                            const bool acc = (kb | kk) != 0;
+                            umma_tf32(tmem + T_A, dS2 + ko, dP + ko, idA, acc);
+                            umma_tf32(tmem + T_C, dS3 + ko, dP + ko, idA, acc);
+                            if (pass == 0) {
+                                umma_tf32(tmem + T_B, dWb + ko, dF + ko, idB, acc);
+                                umma_tf32(tmem + T_D, dW2 + ko, dF + ko, idB, acc);
+                            }
+                        }
+                        umma_commit(&bar_empty[s]);
+                        if (kb == nkb - 1) umma_commit(&bar_gram);
+                        if (kb + PB32_LEAD < nkb) issue_pb(git + PB32_LEAD, kb + PB32_LEAD);
+                    }
+                }
+                __syncwarp();
+            } else {
+                // ----------------------------------------------------------- WORKER warps
+                float E[RPW];
+                uint32_t nbm = 0u;
+#pragma unroll
+                for (int j = 0; j < RPW; ++j) E[j] = 0.f;
+                TileView tv;
+                tv.x = f.x + (size_t)b0 * P; tv.err = f.err + (size_t)b0 * P; tv.mask = f.mask + (size_t)b0 * P;
+                tv.zabs = f.zabs + (size_t)b0 * Nb;
+                tv.nrows = nrows;
+                tv.zero = reinterpret_cast<const uint8_t*>(g.PB + (size_t)nkb * (PB32_KB_BYTES / 4));   // 16 zero bytes after the image
+                RowCursor rc;
+                rc.x = reinterpret_cast<const unsigned char*>(tv.x + (size_t)(RPW * warp) * P + lane);
+                rc.e = reinterpret_cast<const unsigned char*>(tv.err + (size_t)(RPW * warp) * P + lane);
+                rc.m = tv.mask + (size_t)(RPW * warp) * P + lane;
+                rc.z = reinterpret_cast<const unsigned char*>(tv.zabs + (size_t)(RPW * warp) * Nb + lane);
+                KBuf kA, kB;
+#pragma unroll
+                for (int j = 0; j < RPW; ++j) { kA.r[j].z = 0.f; kB.r[j].z = 0.f; }
+                const uint32_t ring_sa = smem_u32(ring) + (uint32_t)warp * 1024u + (uint32_t)lane * 4u;
+                auto run_kblocks = [&](auto nr_tag, auto p0_tag) {
+                    constexpr int NR = decltype(nr_tag)::value;
+                    constexpr bool PASS0 = decltype(p0_tag)::value;
+                    auto load_kb = [&](int kb, KBuf& k) {
+                        const int p0 = kb * KB;
+                        if (p0 + KB <= P) load_kblock<true, true, NR>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
+                        else load_kblock<true, false, NR>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
+                    };
+                    load_kb(0, kA);
+                    if (nkb > 1) load_kb(1, kB);
+                    auto do_kblock = [&](int kb, KBuf& k) {
+                        const uint32_t git = git0 + kb;
+                        const int s = git % NSTAGE32;
+                        const uint32_t u = git / NSTAGE32;
+                        const int p0 = kb * KB;
+                        const bool blue = p0 + lane < Nb;
+                        if (u > 0) mbar_wait_or_trap(&bar_empty[s], (u - 1) & 1);
+                        const uint32_t stage_sa = ring_sa + (uint32_t)s * (uint32_t)STAGE32_BYTES;
+                        const int bm = (p0 + KB <= Nb) ? 1 : (p0 >= Nb ? 0 : 2);
+                        if (bm == 1) kblock_consume32<1, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
+                        else if (bm == 0) kblock_consume32<0, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
+                        else kblock_consume32<2, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
+                        fence_proxy_async();            // MEMBAR.ALL.CTA: before the prefetch below, never after it
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_full[s]);
+                        if (kb + 2 < nkb) load_kb(kb + 2, k);
+                    };
+                    for (int kb = 0; kb < nkb; kb += 2) {
+                        do_kblock(kb, kA);
+                        if (kb + 1 < nkb) do_kblock(kb + 1, kB);
+                    }
+                };
+                if (pass == 0) {
+                    if (nr == RPW) run_kblocks(std::integral_constant<int, RPW>{}, std::true_type{});
+                    else run_kblocks(std::integral_constant<int, 0>{}, std::true_type{});
+#pragma unroll
+                    for (int j = 0; j < RPW; ++j) {
+                        const float e = warp_sum(E[j]);
+                        const bool any = __any_sync(0xffffffffu, (nbm >> j) & 1u);
+                        if (lane == 0) { sE[RPW * warp + j] = e; sNb[RPW * warp + j] = any ? 1.0f : 0.0f; }
+                    }
+                } else {
+                    if (nr == RPW) run_kblocks(std::integral_constant<int, RPW>{}, std::false_type{});
+                    else run_kblocks(std::integral_constant<int, 0>{}, std::false_type{});
+                }
+            }
+            named_bar_sync(1, NTHREADS);            // sE / sNb visible; every worker is done with the ring
+            // ----------------------------------------------------------- drain the accumulators (warps 0..3: lane = spectrum row)
+            if (warp < 4) {
+                mbar_wait_or_trap(&bar_gram, pass_iter & 1);
+                fence_after_sync();
+                const int row = warp * 32 + lane;
+                const bool row_ok = row < nrows;
+                float* dst = g.gram + (size_t)(b0 + (row_ok ? row : 0)) * G32_STRIDE;
+                const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16);
+                for (int c = 0; c < ncol; c += 16) {
+                    float va[16], vc[16];
+                    tmem_ld16(ta + T_A + c, va);
+                    tmem_ld16(ta + T_C + c, vc);
+                    tmem_wait_ld();
+                    if (row_ok) {
+                        float4* da = reinterpret_cast<float4*>(dst + G32_M + pass * SLICE + c);
+                        float4* dc = reinterpret_cast<float4*>(dst + G32_M2 + pass * SLICE + c);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            da[q] = make_float4(va[4 * q], va[4 * q + 1], va[4 * q + 2], va[4 * q + 3]);
+                            dc[q] = make_float4(vc[4 * q], vc[4 * q + 1], vc[4 * q + 2], vc[4 * q + 3]);
+                        }
+                    }
+                }
+                if (pass == 0) {
+                    for (int c = 0; c < H32; c += 16) {
+                        float vb[16], vd[16];
+                        tmem_ld16(ta + T_B + c, vb);
+                        tmem_ld16(ta + T_D + c, vd);
+                        tmem_wait_ld();
+                        if (row_ok) {
+                            float4* db = reinterpret_cast<float4*>(dst + G32_B + c);
+                            float4* dd = reinterpret_cast<float4*>(dst + G32_B2 + c);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                db[q] = make_float4(vb[4 * q], vb[4 * q + 1], vb[4 * q + 2], vb[4 * q + 3]);
+                                dd[q] = make_float4(vd[4 * q], vd[4 * q + 1], vd[4 * q + 2], vd[4 * q + 3]);
+                            }
+                        }
+                    }
+                    if (row_ok) { dst[G32_E] = sE[row]; dst[G32_E + 1] = sNb[row]; }
+                }
+                fence_before_sync();
+            }
+            // pass boundary: the accumulators are drained and every MMA has retired before the next pass overwrites them
+            fence_before_sync();
+            __syncthreads();
+            fence_after_sync();
+        }
+    }
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------
+// k_solve32: one warp per spectrum.  In: scratch row of k_tc_gram32.  Out: NLL, has-blue flag and the hand-off record
+// [a | c | L^-1 | K] (SmallLayout<32>, float) that k_grad<float,32> consumes.           (model.py:132-135, utils.py:29-54)
+// ---------------------------------------------------------------------------------------
+constexpr int SOLVE32_WARPS = 4;
+constexpr int SOLVE32_LD = H32 + 1;
+constexpr int SOLVE32_WARP_DOUBLES = 3 * H32 * SOLVE32_LD + 4 * H32 + 8;
+constexpr int SOLVE32_SMEM = SOLVE32_WARPS * SOLVE32_WARP_DOUBLES * 8;
+
+__global__ void __launch_bounds__(SOLVE32_WARPS * 32) k_solve32(const float* __restrict__ gram, int B, float* __restrict__ small,
+                                                                float* __restrict__ nll, float* __restrict__ hasblue) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* base = reinterpret_cast<double*>(smem_raw) + (size_t)w * SOLVE32_WARP_DOUBLES;
+    double* sM = base;
+    double* sM2 = sM + H32 * SOLVE32_LD;
+    double* sL = sM2 + H32 * SOLVE32_LD;
+    double* sb = sL + H32 * SOLVE32_LD;
+    double* sb2 = sb + H32;
+    double* sa = sb2 + H32;
+    double* sc = sa + H32;
+    double* sout = sc + H32;
+    using SL = SmallLayout<H32>;
+    constexpr int LD = SOLVE32_LD;
+    for (int b = blockIdx.x * SOLVE32_WARPS + w; b < B; b += gridDim.x * SOLVE32_WARPS) {
+        const float* src = gram + (size_t)b * G32_STRIDE;
+        // lane <-> column l: rows k <= l of the packed upper triangle
+        for (int k = 0; k < H32; ++k) {
+            if (lane >= k) {
+                const int n = tri32(k, lane);
+                const double m = (double)__ldg(src + G32_M + n) + (k == lane ? 1.0 : 0.0);      // M = I + Gram
+                const double m2 = (double)__ldg(src + G32_M2 + n);
+                sM[k * LD + lane] = m;  sM[lane * LD + k] = m;
+                sM2[k * LD + lane] = m2; sM2[lane * LD + k] = m2;
+            }
+        }
+        sb[lane] = (double)__ldg(src + G32_B + lane);
+        sb2[lane] = (double)__ldg(src + G32_B2 + lane);
+        const double E = (double)__ldg(src + G32_E);
+        const float hb = __ldg(src + G32_E + 1);
+        __syncwarp();
+        small_algebra<double, H32, true>(sM, sM2, sL, sb, sb2, sa, sc, sout);
+        if (lane == 0) {
+            nll[b] = (float)(0.5 * (E - sout[1] + sout[0]));                                       // model.py:135
+            hasblue[b] = hb;
+        }
+        float* dst = small + (size_t)b * SL::len;
+        for (int e = lane; e < SL::len; e += 32) {
+            double v;
+            if (e < SL::c) v = sa[e];
+            else if (e < SL::Linv) v = sc[e - SL::c];
+            else if (e < SL::K) { const int t = e - SL::Linv; v = sL[(t / H32) * LD + (t % H32)]; }
+            else { const int t = e - SL::K; v = sM2[(t / H32) * LD + (t % H32)]; }
+            dst[e] = (float)v;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace tcg32
+}  // namespace qfa
