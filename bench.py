@@ -289,12 +289,21 @@ def measure_workload(name, args, rank, world, peaks, want_e2e, want_cpu, nspec_o
     value = world * nspec * args.steps / (ms * 1e-3)
     bps = bytes_per_spectrum("predict" if kind == "predict" else "train", grid.Npix, grid.Nb, Nh)
     achieved = nspec * args.steps * bps / (ms * 1e-3) / 1e9        # per GPU, GB/s of algorithmic bytes
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": measured_traffic(kind, grid_name, Nh, nspec),
+            "kernel": kernel_name, "bytes_per_spectrum": bps, "peak_source": peaks["source"]}
+    if Nh > 8 and kind == "train":
+        # Nh = 32 is tensor-bound (AI ~ 330 FLOP/B): algorithmic FLOPs per spectrum
+        # n*[H(H+1)(2+r_b) + 2H^2 + 8H + 30] + 3H^3 against the TF32 tensor peak (= half the measured bf16 peak)
+        n_un = float(M.float().sum() / nspec)
+        r_b = float(M[:, :grid.Nb].float().sum() / max(1.0, float(M.float().sum())))
+        flops = n_un * (Nh * (Nh + 1) * (2 + r_b) + 2 * Nh * Nh + 8 * Nh + 30) + 3 * Nh ** 3
+        tf = nspec * args.steps * flops / (ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": tf, "peak": peaks["tf32_tflops"], "unit": "TFLOP/s",
+                "frac": tf / peaks["tf32_tflops"], "traffic": None, "kernel": kernel_name,
+                "flops_per_spectrum": flops, "peak_source": peaks["tf32_source"]}
     res.update(value=value, ms_per_step=ms / args.steps, clocks=clocks, gpu_launches=launches_per_step * args.steps,
-               roofline={"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": measured_traffic(kind, grid_name, Nh, nspec),
-                         "kernel": kernel_name,
-                         "bytes_per_spectrum": bps, "peak_source": peaks["source"]},
+               roofline=roof,
                config={"workload": name, "kind": kind, "grid": grid_name, "Npix": grid.Npix, "Nb": grid.Nb, "Nh": Nh,
                        "spectra_per_gpu_per_step": nspec, "precision": args.precision,
                        "l2": "inputs per step exceed L2 (%.0f MB)" % (nspec * (9 * grid.Npix + 4 * grid.Nb) / 1e6)})
@@ -333,10 +342,14 @@ def main():
         sys.exit(1)
     rank, world, local = dist_setup(args.gpus)
     torch.cuda.set_device(local)
-    peaks = {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+    peaks = {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)", "tf32_tflops": 1590.0 / 2,
+             "tf32_source": "half of the fallback bf16 peak (B200_PROFILING.md)"}
     pj = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(pj):
-        peaks = {"hbm_gbs": float(json.load(open(pj))["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+        mp = json.load(open(pj))
+        peaks = {"hbm_gbs": float(mp["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)",
+                 "tf32_tflops": float(mp.get("bf16_tflops_sustained", mp.get("bf16_tflops", 1590.0))) / 2,
+                 "tf32_source": "half of the measured sustained bf16 peak (MEASURED_PEAKS.json)"}
     main_res = measure_workload(args.workload, args, rank, world, peaks, not args.no_e2e, not args.no_cpu_baseline,
                                 args.spectra)
     also = {}
