@@ -230,15 +230,16 @@ static Tc32Plan plan_tc32(int Nb, int Nr, int Nh, int B) {
     p.ts = tile_sched(B, 8, &p.ntiles);
     p.npix_tiles = (P + 127) / 128;
     p.ntiles_blue = (Nb + 127) / 128;
-    int want = (4 * num_sms() + p.npix_tiles - 1) / p.npix_tiles;
-    if (want > B) want = B;
+    int want = num_sms() / p.npix_tiles;         // one wave of k_tc_grad32 CTAs
+    const int nsteps = (B + tcg32::G32_SPS - 1) / tcg32::G32_SPS;
+    if (want > nsteps) want = nsteps;
     if (want < 1) want = 1;
     p.nsplit = want;
     const size_t Bn = B > 0 ? B : 1;
     size_t o = 0;
     p.off_pb = o;      o = align_up(o + (size_t)p.nkb * tcg32::PB32_KB_BYTES + 16, 1024);
     p.off_gram = o;    o = align_up(o + Bn * tcg32::G32_STRIDE * 4, 256);
-    p.off_small = o;   o = align_up(o + Bn * SmallLayout<32>::len * 4, 256);
+    p.off_small = o;   o = align_up(o + (Bn + 2) * tcg32::G32_IMG, 1024);      // per-spectrum images for k_tc_grad32 (+2: last step)
     p.off_hasblue = o; o = align_up(o + Bn * 4, 256);
     p.off_nll = o;     o = align_up(o + Bn * 4, 256);
     p.off_part = o;    o = align_up(o + (size_t)p.nsplit * part_len(P, Nb, Nh) * 4, 256);
@@ -451,6 +452,7 @@ static int train_accumulate_tc32(const QfaModel* m, const float* delta, const fl
     if (!attr_done) {
         CK(cudaFuncSetAttribute(k_tc_gram32, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM32_BYTES));
         CK(cudaFuncSetAttribute(k_solve32, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE32_SMEM));
+        CK(cudaFuncSetAttribute(k_tc_grad32, cudaFuncAttributeMaxDynamicSharedMemorySize, G32_SMEM));
         attr_done = true;
     }
     Field<float> f = make_field<float>(m, delta, error, zabs, mask);
@@ -463,9 +465,10 @@ static int train_accumulate_tc32(const QfaModel* m, const float* delta, const fl
     if (sblocks > 2 * num_sms()) sblocks = 2 * num_sms();
     k_solve32<<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, small, nll, hasblue);
     CK(cudaGetLastError());
-    GradArgs<float> gr;
-    gr.f = f; gr.B = B; gr.nsplit = pl.nsplit; gr.small = small; gr.part = part; gr.spart = spart; gr.accumulate = 0;
-    CK(dispatch_grad<float>(32, gr, pl.npix_tiles, st));
+    TcGrad32Args gr;
+    gr.f = f; gr.B = B; gr.nsplit = pl.nsplit; gr.img = small; gr.part = part; gr.spart = spart;
+    k_tc_grad32<<<dim3(pl.npix_tiles, pl.nsplit), G32_THREADS, G32_SMEM, st>>>(gr);
+    CK(cudaGetLastError());
     ReduceArgs<float> ra;
     ra.part = part; ra.spart = spart; ra.nll = nll; ra.hasblue = hasblue; ra.scal = f.scal;
     ra.acc = acc; ra.P = P; ra.Nb = Nb; ra.Nh = Nh; ra.B = B; ra.stride = 1; ra.nsp = (double)B; ra.nsplit = pl.nsplit;

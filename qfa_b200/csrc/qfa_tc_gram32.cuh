@@ -41,6 +41,21 @@ constexpr int T_A = 0, T_C = SLICE, T_B = 2 * SLICE, T_D = 2 * SLICE + H32;
 constexpr int G32_M = 0, G32_M2 = NP2_32, G32_B = 2 * NP2_32, G32_B2 = 2 * NP2_32 + H32, G32_E = 2 * NP2_32 + 2 * H32;
 constexpr int G32_STRIDE = 1124;
 
+// ---- k_tc_grad32 / k_solve32 image geometry
+constexpr int G32_ROWS = 80;                          // image rows per spectrum (UMMA N)
+constexpr int G32_IMG = G32_ROWS * 128;               // 10 240 B
+constexpr int G32_SPS = 3;                            // spectra per step
+constexpr int G32_STAGE = G32_SPS * G32_IMG;          // 30 720 B
+constexpr int G32_NST = 4;                            // image ring stages
+constexpr int G32_W = 12;                             // worker warps
+constexpr int G32_THREADS = (G32_W + 1) * 32;
+constexpr int G32_A_OFF = 0;                          // 16 KB: F rows of the pixel tile
+constexpr int G32_B_OFF = 16384;
+constexpr int G32_RED_OFF = G32_B_OFF + G32_NST * G32_STAGE;        // epilogue: [3 groups][128 pixels][40] floats
+constexpr int G32_SMEM = G32_RED_OFF + 3 * 128 * 40 * 4 + 1024;
+constexpr int G32_TBUF = 256;                         // TMEM columns per buffer (3 x 80 used)
+
+
 __host__ __device__ constexpr int tri32(int k, int l) { return k * H32 - k * (k - 1) / 2 + (l - k); }   // k <= l
 __host__ __device__ constexpr int slice_cols(int p) { return p < 2 ? SLICE : NP2_32 - 2 * SLICE; }
 
@@ -336,7 +351,7 @@ constexpr int SOLVE32_LD = H32 + 1;
 constexpr int SOLVE32_WARP_DOUBLES = 3 * H32 * SOLVE32_LD + 4 * H32 + 8;
 constexpr int SOLVE32_SMEM = SOLVE32_WARPS * SOLVE32_WARP_DOUBLES * 8;
 
-__global__ void __launch_bounds__(SOLVE32_WARPS * 32) k_solve32(const float* __restrict__ gram, int B, float* __restrict__ small,
+__global__ void __launch_bounds__(SOLVE32_WARPS * 32) k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img,
                                                                 float* __restrict__ nll, float* __restrict__ hasblue) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -349,7 +364,6 @@ __global__ void __launch_bounds__(SOLVE32_WARPS * 32) k_solve32(const float* __r
     double* sa = sb2 + H32;
     double* sc = sa + H32;
     double* sout = sc + H32;
-    using SL = SmallLayout<H32>;
     constexpr int LD = SOLVE32_LD;
     for (int b = blockIdx.x * SOLVE32_WARPS + w; b < B; b += gridDim.x * SOLVE32_WARPS) {
         const float* src = gram + (size_t)b * G32_STRIDE;
@@ -373,17 +387,277 @@ __global__ void __launch_bounds__(SOLVE32_WARPS * 32) k_solve32(const float* __r
             nll[b] = (float)(0.5 * (E - sout[1] + sout[0]));                                       // model.py:135
             hasblue[b] = hb;
         }
-        float* dst = small + (size_t)b * SL::len;
-        for (int e = lane; e < SL::len; e += 32) {
-            double v;
-            if (e < SL::c) v = sa[e];
-            else if (e < SL::Linv) v = sc[e - SL::c];
-            else if (e < SL::K) { const int t = e - SL::Linv; v = sL[(t / H32) * LD + (t % H32)]; }
-            else { const int t = e - SL::K; v = sM2[(t / H32) * LD + (t % H32)]; }
-            dst[e] = (float)v;
+        // image for k_tc_grad32 (80 rows x 32, K-major SWIZZLE_128B, TF32): lane = K index
+        float* dst = img + (size_t)b * (G32_IMG / 4);
+        for (int n = 0; n < G32_ROWS; ++n) {
+            double v = 0.0;
+            if (n < H32) v = sM2[lane * LD + n];                 // K^T : B[n][k] = K[k][n]
+            else if (n < 2 * H32) v = sL[(n - H32) * LD + lane];  // L^-1
+            else if (n == 2 * H32) v = sa[lane];
+            else if (n == 2 * H32 + 1) v = sc[lane];
+            dst[sw128_offset(n, lane) / 4] = tf32_rna((float)v);
         }
         __syncwarp();
     }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// k_tc_grad32: pixel-major gradient for 16 < Nh <= 32 with the two big per-cell contractions on the tensor cores
+// ("per-spectrum stacked MMA").  For spectrum b and the CTA's 128-pixel tile:
+//       D_b[i, 0..31]  = sum_l F_il K_b[l][n]        = (f_i^T K_b)_n                 (model.py:137, quirk Q2)
+//       D_b[i, 32..63] = sum_l F_il Linv_b[n][l]     = (L_b^-1 f_i)_n   ->  q_i = |.|^2 = f_i^T M_b^-1 f_i   (model.py:136)
+//       D_b[i, 64]     = sum_l F_il a_b[l]           = f_i^T hmean_b                 (model.py:136)
+//   A = the tile's rows of F (one 128 x 32 K-major tile, built once per CTA), B = the 80-row image of spectrum b that
+//   k_solve32 writes (rows 0..31 K^T, 32..63 L^-1, 64 a, 65 c, rest 0), accumulators in TMEM: 2 buffers x 3 spectra x 80
+//   columns.  13 warps: 12 workers = 4 TMEM lane quadrants x 3 groups, group g owns spectrum 3n+g of step n (one cell per
+//   thread and step), + the control warp (bulk copies of the images, every tcgen05.mma).
+//   gradF_ik = f_ik sum_b s3_bi - sum_b [ s2_bi (f_i^T K_b)_k + (A u)_bi c_bk ] accumulates in 32 registers per thread.
+// ---------------------------------------------------------------------------------------
+struct TcGrad32Args {
+    Field<float> f;
+    int B;
+    int nsplit;            // CTAs per pixel tile; grid = (npix_tiles, nsplit)
+    const float* img;      // [B (+2 pad)][G32_IMG/4]  images written by k_solve32
+    float* part;           // [nsplit][part_len]
+    float* spart;          // [nsplit][npix_tiles][3]
+};
+
+__global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args g) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* sm = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar_b[G32_NST], bar_tm_full[2], bar_tm_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float sred2[3 * 32];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int quad = warp & 3, grp = warp >> 2;                   // workers: grp 0..2
+    const Field<float>& f = g.f;
+    const int P = f.P, Nb = f.Nb, Nh = f.Nh;
+    const int pt = blockIdx.x;
+    // spectra range of this CTA, in whole steps of 3
+    const int nsteps_all = (g.B + G32_SPS - 1) / G32_SPS;
+    const int st0 = (int)((long long)blockIdx.y * nsteps_all / g.nsplit);
+    const int st1 = (int)((long long)(blockIdx.y + 1) * nsteps_all / g.nsplit);
+    const int nst = st1 - st0;
+
+    if (tid == 0) {
+        for (int s = 0; s < G32_NST; ++s) mbar_init(&bar_b[s], 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&bar_tm_full[s], 1); mbar_init(&bar_tm_empty[s], G32_W); }
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+    const int pi = quad * 32 + lane;                 // pixel row inside the tile = TMEM lane
+    const int i = pt * 128 + pi;
+    const bool pix_ok = i < P;
+    // A operand: this tile's rows of F, TF32, K-major SWIZZLE_128B (row = pixel); written by the 4 warps of group 0
+    if (warp < 4) {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = c4 * 4 + q;
+                v[q] = (pix_ok && k < Nh) ? tf32_rna(__ldg(f.F + (size_t)i * Nh + k)) : 0.0f;
+            }
+            sts_v4(smem_u32(sm) + G32_A_OFF + sw128_offset(pi, c4 * 4), v[0], v[1], v[2], v[3]);
+        }
+        fence_proxy_async();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t sm_sa = smem_u32(sm);
+    const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16);
+
+    float gF[H32];
+#pragma unroll
+    for (int k = 0; k < H32; ++k) gF[k] = 0.f;
+    float gPsi = 0.f, cnt = 0.f, dmu = 0.f, s3sum = 0.f, gOm = 0.f, sc0 = 0.f, sc1 = 0.f, sc2 = 0.f;
+
+    if (warp == G32_W) {
+        // =============================================================== CONTROL warp
+        if (nst > 0 && elect_one()) {
+            const uint32_t idN = idesc_tf32(128, G32_ROWS);
+            auto issue_b = [&](int n) {           // images of step n -> ring stage n % 4
+                const int s = n % G32_NST;
+                const size_t b0 = (size_t)(st0 + n) * G32_SPS;
+                mbar_expect_tx(&bar_b[s], G32_STAGE);
+                bulk_g2s(sm + G32_B_OFF + s * G32_STAGE, g.img + b0 * (G32_IMG / 4), G32_STAGE, &bar_b[s]);
+            };
+            for (int n = 0; n < 2 && n < nst; ++n) issue_b(n);
+            const uint64_t dA = desc_sw128_kmajor(sm_sa + G32_A_OFF);
+            for (int n = 0; n < nst; ++n) {
+                const int buf = n & 1, s = n % G32_NST;
+                // workers have drained TMEM buffer `buf` (step n-2): its MMAs retired long ago, so ring stage (n+2) % 4 = (n-2) % 4 is free
+                if (n >= 2) mbar_wait_or_trap(&bar_tm_empty[buf], ((n >> 1) - 1) & 1);
+                if (n + 2 < nst) issue_b(n + 2);
+                mbar_wait_or_trap(&bar_b[s], (n / G32_NST) & 1);
+                fence_after_sync();
+#pragma unroll
+                for (int sp = 0; sp < G32_SPS; ++sp) {
+                    const uint64_t dB = desc_sw128_kmajor(sm_sa + G32_B_OFF + s * G32_STAGE + sp * G32_IMG);
+                    const uint32_t dcol = tmem + buf * G32_TBUF + sp * G32_ROWS;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) umma_tf32(dcol, dA + (uint64_t)(2 * kk), dB + (uint64_t)(2 * kk), idN, kk > 0);
+                }
+                umma_commit(&bar_tm_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================================================== WORKER warps
+        const int ic = pix_ok ? i : P - 1;
+        const bool blue = pix_ok && i < Nb;
+        const bool any_blue = pt * 128 + quad * 32 < Nb;  // warp-uniform
+        const int iz = i < Nb ? i : (Nb > 0 ? Nb - 1 : 0);
+        const float psi = __ldg(f.Psi + ic);
+        const float om = blue ? __ldg(f.omega + i) : 0.0f;
+        const float tau0 = __ldg(f.scal + 0), c0s = __ldg(f.scal + 1), beta = __ldg(f.scal + 2);
+        const float one_m_c0 = 1.0f - c0s, nt0l2e = -tau0 * kLog2e, l2zn = f.llogzn * kLog2e;
+        struct Cell { float x, e, z; unsigned m; };
+        auto load_cell = [&](int n, Cell& c) {
+            const int b = (st0 + n) * G32_SPS + grp;
+            if (pix_ok && b < g.B) {
+                const size_t o = (size_t)b * P + i;
+                c.m = ldg_stream_u8(f.mask + o);
+                c.x = ldg_stream(f.x + o);
+                c.e = ldg_stream(f.err + o);
+                c.z = any_blue ? ldg_stream(f.zabs + (size_t)b * Nb + iz) : 0.f;
+            } else { c.m = 0u; c.x = 0.f; c.e = 1.f; c.z = 0.f; }
+        };
+        Cell cA, cB;
+        if (nst > 0) load_cell(0, cA);
+        if (nst > 1) load_cell(1, cB);
+        auto do_step = [&](int n, Cell& cb) {
+            const int buf = n & 1, s = n % G32_NST;
+            const int b = (st0 + n) * G32_SPS + grp;
+            const bool valid = b < g.B;                       // warp-uniform
+            mbar_wait_or_trap(&bar_tm_full[buf], (n >> 1) & 1);
+            fence_after_sync();
+            const uint32_t tcol = ta + buf * G32_TBUF + grp * G32_ROWS;
+            float q = 0.f, fa = 0.f;
+            {
+                float z[16];
+                tmem_ld16(tcol + 32, z); tmem_wait_ld();
+#pragma unroll
+                for (int t = 0; t < 16; ++t) q = fmaf(z[t], z[t], q);
+                tmem_ld16(tcol + 48, z); tmem_wait_ld();
+#pragma unroll
+                for (int t = 0; t < 16; ++t) q = fmaf(z[t], z[t], q);
+                float w8[8];
+                tmem_ld8(tcol + 64, w8); tmem_wait_ld();
+                fa = w8[0];
+            }
+            const bool mk = cb.m != 0u && valid;
+            float A = 1.0f, zdep = 0.0f, powb = 0.0f, L2 = 0.0f;
+            if (any_blue) {
+                L2 = lg2f(1.0f + (mk ? cb.z : 0.0f));
+                const float tau = fmaf(f.lt0, ex2f(f.lbe * (L2 - l2zn)), f.lC);       // utils.py:106 etc.
+                const float Ab = ex2f(-kLog2e * tau);                                   // model.py:125
+                powb = ex2f(beta * L2);                                                 // utils.py:72
+                const float root = one_m_c0 - ex2f(nt0l2e * powb);                      // utils.py:91
+                A = blue ? Ab : 1.0f;
+                zdep = root * root;
+            }
+            const float A2 = A * A;
+            const float oz = om * zdep;
+            const float D = fmaf(A2, psi, fmaf(cb.e, cb.e, oz));                        // model.py:128-131
+            const float w = mk ? rcpf(D) : 0.0f;
+            const float r = mk ? cb.x : 0.0f;
+            const float u = w * fmaf(-A, fa, r);                                        // (Sigma^-1 delta)_i
+            const float s2 = w * A2;
+            const float gd = 0.5f * (w - w * s2 * q - u * u);                           // model.py:136,138
+            const float Au = A * u;
+            if (valid) {                                       // an absent spectrum has no image: its TMEM columns are garbage
+                gPsi = fmaf(A2, gd, gPsi);                                              // model.py:139
+                cnt += mk ? 1.0f : 0.0f;
+                dmu -= Au;
+                s3sum = fmaf(s2, A, s3sum);
+                if (any_blue) {
+                    gOm = fmaf(gd, zdep, gOm);                                          // model.py:140
+                    const float rootl = 1.0f - tau0 * powb - c0s;                       // model.py:141 (quirk Q3)
+                    const float t = gd * oz * zdep * 2.0f * rootl;
+                    sc0 = fmaf(-t, powb, sc0);                                          // model.py:142
+                    sc1 -= t;                                                           // model.py:144
+                    sc2 = fmaf(-t, tau0 * powb * (L2 * kLn2), sc2);                     // model.py:143
+                }
+                // gradF: - s2 (f^T K)_k - (A u) c_k ; c_b = image row 65 (shared memory, broadcast reads)
+                const uint32_t crow = sm_sa + G32_B_OFF + (uint32_t)s * G32_STAGE + (uint32_t)grp * G32_IMG;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float y[16];
+                    tmem_ld16(tcol + 16 * h, y); tmem_wait_ld();
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        float cx, cy, cz, cw;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cx), "=f"(cy), "=f"(cz), "=f"(cw)
+                                     : "r"(crow + sw128_offset(65, 16 * h + 4 * c4)));
+                        gF[16 * h + 4 * c4 + 0] -= fmaf(s2, y[4 * c4 + 0], Au * cx);
+                        gF[16 * h + 4 * c4 + 1] -= fmaf(s2, y[4 * c4 + 1], Au * cy);
+                        gF[16 * h + 4 * c4 + 2] -= fmaf(s2, y[4 * c4 + 2], Au * cz);
+                        gF[16 * h + 4 * c4 + 3] -= fmaf(s2, y[4 * c4 + 3], Au * cw);
+                    }
+                }
+            }
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tm_empty[buf]);
+            if (n + 2 < nst) load_cell(n + 2, cb);
+        };
+        for (int n = 0; n < nst; n += 2) {
+            do_step(n, cA);
+            if (n + 1 < nst) do_step(n + 1, cB);
+        }
+    }
+
+    // ---- end of the CTA: fold the three groups, finish gradF, write the per-split partials
+    float* part = g.part + (size_t)blockIdx.y * part_len(P, Nb, Nh);
+    float* red = reinterpret_cast<float*>(sm + G32_RED_OFF);     // [3 grp][128 pixels][40]
+    fence_before_sync();
+    __syncthreads();
+    if (warp < G32_W) {
+        float* r = red + ((size_t)grp * 128 + pi) * 40;
+#pragma unroll
+        for (int k = 0; k < H32; ++k) r[k] = gF[k];
+        r[32] = gPsi; r[33] = cnt; r[34] = dmu; r[35] = s3sum; r[36] = gOm; r[37] = sc0; r[38] = sc1; r[39] = sc2;
+    }
+    __syncthreads();
+    float sc3[3] = {0.f, 0.f, 0.f};
+    if (warp < 4) {
+        float v[40];
+#pragma unroll
+        for (int q = 0; q < 40; ++q)
+            v[q] = red[((size_t)0 * 128 + pi) * 40 + q] + red[((size_t)1 * 128 + pi) * 40 + q] + red[((size_t)2 * 128 + pi) * 40 + q];
+        if (pix_ok) {
+            float* pF = part + (size_t)i * Nh;
+            float* pPsi = part + (size_t)P * Nh + i;
+            float* pOm = part + (size_t)P * Nh + P + i;
+            float* pCnt = part + (size_t)P * Nh + P + Nb + i;
+            float* pMu = part + (size_t)P * Nh + 2 * (size_t)P + Nb + i;
+#pragma unroll
+            for (int k = 0; k < H32; ++k)
+                if (k < Nh) pF[k] = fmaf(__ldg(f.F + (size_t)i * Nh + k), v[35], v[k]);      // model.py:137 (quirk Q2)
+            *pPsi = v[32]; *pCnt = v[33]; *pMu = v[34];
+            if (i < Nb) *pOm = v[36];
+        }
+        sc3[0] = v[37]; sc3[1] = v[38]; sc3[2] = v[39];
+    }
+    if (pt * 128 < Nb) {
+        float a0 = warp_sum(sc3[0]), a1 = warp_sum(sc3[1]), a2 = warp_sum(sc3[2]);
+        if (lane == 0 && warp < 4) { sred2[warp] = a0; sred2[32 + warp] = a1; sred2[64 + warp] = a2; }
+        __syncthreads();
+        if (tid < 3) {
+            float t = 0.f;
+            for (int w = 0; w < 4; ++w) t += sred2[tid * 32 + w];
+            g.spart[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3 + tid] = t;
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace tcg32
