@@ -462,7 +462,7 @@ static int train_accumulate_tc32(const QfaModel* m, const float* delta, const fl
     k_tc_gram32<<<grid, tcg::NTHREADS, SMEM32_BYTES, st>>>(a);
     CK(cudaGetLastError());
     int sblocks = (B + SOLVE32_WARPS - 1) / SOLVE32_WARPS;
-    if (sblocks > 2 * num_sms()) sblocks = 2 * num_sms();
+    if (sblocks > 3 * num_sms()) sblocks = 3 * num_sms();        // 3 CTAs (12 warps) per SM fit
     k_solve32<<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, small, nll, hasblue);
     CK(cudaGetLastError());
     TcGrad32Args gr;

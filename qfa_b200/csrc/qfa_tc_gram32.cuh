@@ -348,59 +348,115 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
 // ---------------------------------------------------------------------------------------
 constexpr int SOLVE32_WARPS = 4;
 constexpr int SOLVE32_LD = H32 + 1;
-constexpr int SOLVE32_WARP_DOUBLES = 3 * H32 * SOLVE32_LD + 4 * H32 + 8;
-constexpr int SOLVE32_SMEM = SOLVE32_WARPS * SOLVE32_WARP_DOUBLES * 8;
+constexpr int SOLVE32_WARP_DOUBLES = 2 * H32 * SOLVE32_LD + 2 * H32 + 8;      // M / M^-1, L^-1, b, a
+constexpr int SOLVE32_SMEM = SOLVE32_WARPS * SOLVE32_WARP_DOUBLES * 8;        // 17.4 KB per warp -> 12 warps per SM
 
 __global__ void __launch_bounds__(SOLVE32_WARPS * 32) k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img,
                                                                 float* __restrict__ nll, float* __restrict__ hasblue) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double* base = reinterpret_cast<double*>(smem_raw) + (size_t)w * SOLVE32_WARP_DOUBLES;
-    double* sM = base;
-    double* sM2 = sM + H32 * SOLVE32_LD;
-    double* sL = sM2 + H32 * SOLVE32_LD;
+    double* sM = base;                              // M -> L -> M^-1
+    double* sL = sM + H32 * SOLVE32_LD;             // L^-1 (lower)
     double* sb = sL + H32 * SOLVE32_LD;
-    double* sb2 = sb + H32;
-    double* sa = sb2 + H32;
-    double* sc = sa + H32;
-    double* sout = sc + H32;
+    double* sa = sb + H32;
     constexpr int LD = SOLVE32_LD;
     for (int b = blockIdx.x * SOLVE32_WARPS + w; b < B; b += gridDim.x * SOLVE32_WARPS) {
         const float* src = gram + (size_t)b * G32_STRIDE;
+        float* dst = img + (size_t)b * (G32_IMG / 4);
         // lane <-> column l: rows k <= l of the packed upper triangle
         for (int k = 0; k < H32; ++k) {
             if (lane >= k) {
-                const int n = tri32(k, lane);
-                const double m = (double)__ldg(src + G32_M + n) + (k == lane ? 1.0 : 0.0);      // M = I + Gram
-                const double m2 = (double)__ldg(src + G32_M2 + n);
+                const double m = (double)__ldg(src + G32_M + tri32(k, lane)) + (k == lane ? 1.0 : 0.0);      // M = I + Gram
                 sM[k * LD + lane] = m;  sM[lane * LD + k] = m;
-                sM2[k * LD + lane] = m2; sM2[lane * LD + k] = m2;
             }
         }
         sb[lane] = (double)__ldg(src + G32_B + lane);
-        sb2[lane] = (double)__ldg(src + G32_B2 + lane);
-        const double E = (double)__ldg(src + G32_E);
-        const float hb = __ldg(src + G32_E + 1);
-        __syncwarp();
-        small_algebra<double, H32, true>(sM, sM2, sL, sb, sb2, sa, sc, sout);
-        if (lane == 0) {
-            nll[b] = (float)(0.5 * (E - sout[1] + sout[0]));                                       // model.py:135
-            hasblue[b] = hb;
+        // column `lane` of M2 (symmetric) straight into registers
+        double m2c[H32];
+#pragma unroll
+        for (int k = 0; k < H32; ++k) {
+            const int lo = k < lane ? k : lane, hi = k < lane ? lane : k;
+            m2c[k] = (double)__ldg(src + G32_M2 + tri32(lo, hi));
         }
-        // image for k_tc_grad32 (80 rows x 32, K-major SWIZZLE_128B, TF32): lane = K index
-        float* dst = img + (size_t)b * (G32_IMG / 4);
-        for (int n = 0; n < G32_ROWS; ++n) {
-            double v = 0.0;
-            if (n < H32) v = sM2[lane * LD + n];                 // K^T : B[n][k] = K[k][n]
-            else if (n < 2 * H32) v = sL[(n - H32) * LD + lane];  // L^-1
-            else if (n == 2 * H32) v = sa[lane];
-            else if (n == 2 * H32 + 1) v = sc[lane];
-            dst[sw128_offset(n, lane) / 4] = tf32_rna((float)v);
+        __syncwarp();
+        // ---- right-looking Cholesky, lane <-> row
+        double logdet = 0.0;
+        for (int j = 0; j < H32; ++j) {
+            const double d = sqrt(sM[j * LD + j]);
+            logdet += log(d);
+            const double inv = 1.0 / d;
+            __syncwarp();
+            if (lane == j) sM[j * LD + j] = d;
+            if (lane > j) sM[lane * LD + j] *= inv;
+            __syncwarp();
+            if (lane > j) {
+                const double lij = sM[lane * LD + j];
+                for (int k = j + 1; k <= lane; ++k) sM[lane * LD + k] -= lij * sM[k * LD + j];
+            }
+            __syncwarp();
+        }
+        logdet *= 2.0;
+        // ---- column `lane` of L^-1 in registers; image rows 32..63 (row n, K index = lane) come straight from them
+        double x[H32];
+#pragma unroll
+        for (int r = 0; r < H32; ++r) {
+            double sacc = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < r; ++k) sacc -= sM[r * LD + k] * x[k];
+            x[r] = sacc / sM[r * LD + r];
+        }
+#pragma unroll
+        for (int r = 0; r < H32; ++r) {
+            sL[r * LD + lane] = x[r];
+            dst[sw128_offset(H32 + r, lane) / 4] = tf32_rna((float)x[r]);
+        }
+        __syncwarp();
+        {                                                    // M^-1 = L^-T L^-1, lane <-> column
+            double col[H32];
+#pragma unroll
+            for (int r = 0; r < H32; ++r) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int k = r; k < H32; ++k) sacc += sL[k * LD + r] * x[k];
+                col[r] = sacc;
+            }
+#pragma unroll
+            for (int r = 0; r < H32; ++r) sM[r * LD + lane] = col[r];
+        }
+        __syncwarp();
+        double av = 0.0;
+        for (int k = 0; k < H32; ++k) av += sM[lane * LD + k] * sb[k];                 // a = M^-1 b
+        sa[lane] = av;
+        double quad = av * sb[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) quad += __shfl_xor_sync(0xffffffffu, quad, o);
+        dst[sw128_offset(2 * H32, lane) / 4] = tf32_rna((float)av);
+        __syncwarp();
+        {                                                    // c = b2 - M2 a  (M2 symmetric: row `lane` = column `lane`)
+            double cv = (double)__ldg(src + G32_B2 + lane);
+#pragma unroll
+            for (int k = 0; k < H32; ++k) cv -= m2c[k] * sa[k];
+            dst[sw128_offset(2 * H32 + 1, lane) / 4] = tf32_rna((float)cv);
+        }
+        // ---- K = M^-1 M2, column `lane`; image rows 0..31: B[n][k] = K[k][n] -> row n = lane's column, K index = k
+        //      i.e. this lane writes K[r][lane] to image row `lane`, position r
+#pragma unroll
+        for (int r = 0; r < H32; ++r) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < H32; ++k) sacc += sM[r * LD + k] * m2c[k];
+            dst[sw128_offset(lane, r) / 4] = tf32_rna((float)sacc);
+        }
+        for (int n = 2 * H32 + 2; n < G32_ROWS; ++n) dst[sw128_offset(n, lane) / 4] = 0.0f;
+        if (lane == 0) {
+            const double E = (double)__ldg(src + G32_E);
+            nll[b] = (float)(0.5 * (E - quad + logdet));                                       // model.py:135
+            hasblue[b] = __ldg(src + G32_E + 1);
         }
         __syncwarp();
     }
 }
-
 
 // ---------------------------------------------------------------------------------------
 // k_tc_grad32: pixel-major gradient for 16 < Nh <= 32 with the two big per-cell contractions on the tensor cores
