@@ -257,9 +257,9 @@ def measure_workload(name, args, rank, world, peaks, want_e2e, want_cpu, nspec_o
             launches_per_step = 5
             kernel_name = "k_tc_gram<TRAIN> + k_tc_grad (tcgen05) + k_reduce + k_adam"
         elif 16 < Nh <= 32 and args.precision == "mixed":
-            # k_tc_build_images32, k_tc_gram32, k_solve32, k_grad<float,32>, k_reduce, k_adam
+            # k_tc_build_images32, k_tc_gram32, k_solve32, k_tc_grad32, k_reduce, k_adam
             launches_per_step = 6
-            kernel_name = "k_tc_gram32 (tcgen05, 3 passes) + k_solve32 + k_grad<float,32> (CUDA cores) + k_reduce + k_adam"
+            kernel_name = "k_tc_gram32 (tcgen05, 3 passes) + k_solve32 + k_tc_grad32 (tcgen05) + k_reduce + k_adam"
         else:
             n_sub = -(-nspec // max(1, min(nspec, (48 << 20) // (9 * grid.Npix + 4 * grid.Nb))))
             launches_per_step = 2 * n_sub + 1 + 1
