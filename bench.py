@@ -149,6 +149,9 @@ def dist_setup(n):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
+        # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION: keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
 
