@@ -48,7 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + SOURCES + ["-o", LIB_PATH + ".tmp"]
+    extra = ["-DQFA_ENABLE_TRACE"] if os.environ.get("QFA_ENABLE_TRACE") else []     # clock64 stamps for scratch/*_trace.py
+    cmd = [nvcc] + NVCC_FLAGS + extra + SOURCES + ["-o", LIB_PATH + ".tmp"]
     if verbose:
         print(" ".join(cmd))
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,4 +1,4 @@
-"""GPU scratch: clock64 trace of k_tc_gram (CTA 0, first tile): where do the warps wait?"""
+"""GPU scratch (build the library with QFA_ENABLE_TRACE=1 first: python -c "from qfa_b200 import _lib; _lib.build(force=True)"): clock64 trace of k_tc_gram (CTA 0, first tile): where do the warps wait?"""
 import sys, ctypes, numpy as np, torch
 sys.path.insert(0, '/root/repo')
 from qfa_b200 import QFA, synth, _lib
