@@ -259,7 +259,7 @@ def measure_workload(name, args, rank, world, peaks, want_e2e, want_cpu, nspec_o
             # k_tc_build_images, k_tc_gram<TRAIN>, k_tc_grad, k_reduce, k_adam
             launches_per_step = 5
             kernel_name = "k_tc_gram<TRAIN> + k_tc_grad (tcgen05) + k_reduce + k_adam"
-        elif 16 < Nh <= 32 and args.precision == "mixed":
+        elif 8 < Nh <= 32 and args.precision == "mixed":
             # k_tc_build_images32, k_tc_gram32, k_solve32, k_tc_grad32, k_reduce, k_adam
             launches_per_step = 6
             kernel_name = "k_tc_gram32 (tcgen05, 3 passes) + k_solve32 + k_tc_grad32 (tcgen05) + k_reduce + k_adam"

@@ -36,9 +36,9 @@ extern "C" {
 /* precision modes */
 #define QFA_PREC_FP64 0 /* double everywhere; parity mode (<=1e-5 vs fp64-promoted reference) */
 #define QFA_PREC_FP32 1 /* float CUDA-core arithmetic (the reference itself is a float32 program) */
-#define QFA_PREC_TF32 2 /* "mixed": float everywhere; for Nh <= 8 and batches >= QFA_TC_MIN_BATCH the contractions
-                           (weighted Grams, continuum/sigma, gradient) run on the tensor cores (tcgen05 kind::tf32,
-                           operands rounded to TF32, fp32 accumulation in TMEM) */
+#define QFA_PREC_TF32 2 /* "mixed": float everywhere; for batches >= QFA_TC_MIN_BATCH the contractions (weighted Grams,
+                           continuum/sigma, gradient) run on the tensor cores (tcgen05 kind::tf32, operands rounded to
+                           TF32, fp32 accumulation in TMEM): Nh <= 8 train + predict, 8 < Nh <= 32 train */
 
 /* mean optical depth laws, reference QFA/utils.py:95-141,149-171 (series = 1) */
 #define QFA_TAU_BECKER 0
@@ -48,7 +48,7 @@ extern "C" {
 
 /* flags */
 #define QFA_FLAG_ZERO_ACC 1     /* qfa_train_accumulate: clear `acc` before accumulating */
-#define QFA_FLAG_FORCE_TENSOR 2 /* QFA_PREC_TF32 with Nh <= 8: use the tcgen05 kernels even for batches smaller than
+#define QFA_FLAG_FORCE_TENSOR 2 /* QFA_PREC_TF32: use the tcgen05 kernels even for batches smaller than
                                    QFA_TC_MIN_BATCH (env, default 1024) spectra */
 
 /* error codes (negative) */

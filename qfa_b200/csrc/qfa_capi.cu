@@ -216,13 +216,13 @@ static TcTrainPlan plan_tc_train(int Nb, int Nr, int Nh, int B) {
     return p;
 }
 
-// ---- tensor-core Grams for 16 < Nh <= 32 (QFA_PREC_TF32): k_tc_gram32 + k_solve32, then the float k_grad
+// ---- tensor-core train path for 8 < Nh <= 32 (QFA_PREC_TF32): k_tc_gram32 + k_solve32 + k_tc_grad32
 struct Tc32Plan {
     int nkb, ntiles, npix_tiles, nsplit, ntiles_blue;
     tcg::TileSched ts;
     size_t off_pb, off_gram, off_small, off_hasblue, off_nll, off_part, off_spart, total;
 };
-static inline bool tc32_eligible(int Nh, int precision) { return precision == QFA_PREC_TF32 && Nh > 16 && Nh <= 32; }
+static inline bool tc32_eligible(int Nh, int precision) { return precision == QFA_PREC_TF32 && Nh > tcg::HP && Nh <= 32; }   // zero-padded to 32
 static Tc32Plan plan_tc32(int Nb, int Nr, int Nh, int B) {
     Tc32Plan p;
     const int P = Nb + Nr;

@@ -440,40 +440,44 @@ def test_smooth_clip_prepare_kernels(cuda_model_factory):
     assert np.abs(delta.cpu().numpy()[ok] - d["delta"].numpy()[ok]).max() < 1e-5
 
 
-# ----------------------------------------------------------------------------- tensor-core Grams at Nh = 32
+# ----------------------------------------------------------------------------- tensor-core train path for 8 < Nh <= 32
 def test_tensor_core_nh32_train_path(cuda_model_factory):
-    """16 < Nh <= 32: k_tc_gram32 (three tcgen05 passes over the 528 Khatri-Rao columns) + k_solve32 + k_grad<float,32>.
-    (a) the reference golden of the Npix 1000 / Nh 32 case, forced onto the tensor-core path;
-    (b) a ragged 3 000-spectra synthetic batch against the float CUDA-core path of the same library (which is itself
-        pinned to the goldens).  Single-pass TF32 operands (2^-11) and a Gram whose condition number is ~1e3 for these
-        random smooth factors: the per-spectrum NLL (a cancelling difference, model.py:135) scatters by up to ~2e-3 per
-        unmasked pixel around the float result (measured: max 5.5e-3, median 2.6e-4), WITHOUT bias -- the batch loss agrees
-        to 1e-4 per pixel (measured 5e-5); gradients to 5e-2 max-norm (measured: F 3.3e-2, the others <= 5e-3)."""
-    c, g = load_case("l32", "f64")
-    m = cuda_model_factory(c, "tf32")
-    loss, grads = m.forward(dev(c["delta"]), dev(c["error"]), dev(c["zabs"]), dev(c["mask"]))
-    npx = np.maximum(1, c["mask"].sum(1))
-    assert abs(float(loss) - float(np.squeeze(g["loss"]))) <= 1e-2 * npx.mean()
-    for k in KEYS:
-        assert relerr(grads[k].cpu().numpy(), g["grad_" + k]) < 5e-2, k
+    """8 < Nh <= 32 (zero-padded to 32): k_tc_gram32 (three tcgen05 passes over the 528 Khatri-Rao columns) + k_solve32 +
+    k_tc_grad32 (per-spectrum stacked MMAs).
+    (a) reference goldens forced onto the tensor-core path: the Npix 1000 / Nh 32 case at the usual tensor-core bound, and
+        the 96-pixel Nh = 12 / 16 cases (random unit-scale factors: 8 pixels per factor, badly conditioned M) which pin the
+        padding logic -- their gradF carries the amplified TF32 operand rounding (measured 0.18), everything else <= 5e-2;
+    (b) ragged 3 001-spectra synthetic batches (1000 pixels; Nh = 12 and 32) against the float CUDA-core path of the same
+        library (itself pinned to the goldens).  Single-pass TF32 operands (2^-11) and cond(M) ~ 1e3: the per-spectrum NLL
+        (a cancelling difference, model.py:135) scatters by up to ~5.5e-3 per unmasked pixel (median 2.6e-4) WITHOUT bias --
+        the batch loss agrees to 1e-4 per pixel; gradF to 3.3e-2 max-norm, the other gradients to <= 6.5e-3."""
+    for name, tolF in (("l32", 5e-2), ("tiny12", 3e-1), ("tiny16", 3e-1)):
+        c, g = load_case(name, "f64")
+        m = cuda_model_factory(c, "tf32")
+        loss, grads = m.forward(dev(c["delta"]), dev(c["error"]), dev(c["zabs"]), dev(c["mask"]))
+        npx = np.maximum(1, c["mask"].sum(1))
+        assert abs(float(loss) - float(np.squeeze(g["loss"]))) <= 1e-2 * npx.mean(), name
+        for k in KEYS:
+            assert relerr(grads[k].cpu().numpy(), g["grad_" + k]) < (tolF if k == "F" else 5e-2), (name, k)
     from qfa_b200 import QFA, synth
     grid = synth.GRIDS["l32"]
-    P, mu = synth.smooth_random_params(grid, 32, seed=1237)
-    d = synth.make_spectra(P, mu, grid, 3001, seed=11, device=torch.device("cuda:0"), mask_iid=0.15, run_len=(40, 160))
-    Pn = {k: v.numpy() for k, v in P.items()}
-    out = {}
-    for prec in ("fp32", "tf32"):
-        mm = QFA(grid.Nb, grid.Nr, 32, torch.device("cuda:0"), model_params=Pn, precision=prec)
-        nll = torch.empty(3001, device="cuda")
-        mm.accumulate(d["delta"], d["error"], d["zabs"], d["mask"], nll_out=nll)
-        l, gr = mm.forward(d["delta"], d["error"], d["zabs"], d["mask"])
-        out[prec] = (float(l), {k: gr[k].cpu().numpy() for k in KEYS}, nll.cpu().numpy())
-    npx = np.maximum(1, d["mask"].sum(1).cpu().numpy())
-    dn = np.abs(out["tf32"][2] - out["fp32"][2]) / npx
-    ge = {k: relerr(out["tf32"][1][k], out["fp32"][1][k]) for k in KEYS}
-    print("nh32 tf32 vs fp32: loss diff / px %.2e, per-spectrum NLL / px max %.2e median %.2e, grads %s" % (
-        abs(out["tf32"][0] - out["fp32"][0]) / npx.mean(), dn.max(), np.median(dn), {k: "%.1e" % v for k, v in ge.items()}))
-    assert abs(out["tf32"][0] - out["fp32"][0]) <= 1e-4 * npx.mean()
-    assert dn.max() <= 1e-2 and np.median(dn) <= 1e-3
-    for k in KEYS:
-        assert ge[k] < 5e-2, k
+    for Nh in (12, 32):
+        P, mu = synth.smooth_random_params(grid, Nh, seed=1237)
+        d = synth.make_spectra(P, mu, grid, 3001, seed=11, device=torch.device("cuda:0"), mask_iid=0.15, run_len=(40, 160))
+        Pn = {k: v.numpy() for k, v in P.items()}
+        out = {}
+        for prec in ("fp32", "tf32"):
+            mm = QFA(grid.Nb, grid.Nr, Nh, torch.device("cuda:0"), model_params=Pn, precision=prec)
+            nll = torch.empty(3001, device="cuda")
+            mm.accumulate(d["delta"], d["error"], d["zabs"], d["mask"], nll_out=nll)
+            l, gr = mm.forward(d["delta"], d["error"], d["zabs"], d["mask"])
+            out[prec] = (float(l), {k: gr[k].cpu().numpy() for k in KEYS}, nll.cpu().numpy())
+        npx = np.maximum(1, d["mask"].sum(1).cpu().numpy())
+        dn = np.abs(out["tf32"][2] - out["fp32"][2]) / npx
+        ge = {k: relerr(out["tf32"][1][k], out["fp32"][1][k]) for k in KEYS}
+        print("Nh %d tf32 vs fp32: loss diff / px %.2e, per-spectrum NLL / px max %.2e median %.2e, grads %s" % (
+            Nh, abs(out["tf32"][0] - out["fp32"][0]) / npx.mean(), dn.max(), np.median(dn), {k: "%.1e" % v for k, v in ge.items()}))
+        assert abs(out["tf32"][0] - out["fp32"][0]) <= 1e-4 * npx.mean()
+        assert dn.max() <= 1e-2 and np.median(dn) <= 1e-3
+        for k in KEYS:
+            assert ge[k] < (5e-2 if k == "F" else 1e-2), k
