@@ -9,5 +9,6 @@ from ._lib import QfaError, build, lib  # noqa: F401
 from .model import QFA  # noqa: F401
 from .optimizer import Adam, step_scheduler  # noqa: F401
 from .utils import tau, default_tau  # noqa: F401
+from .dataloader import DeviceDataloader  # noqa: F401
 
 __version__ = "0.1.0"

@@ -481,3 +481,35 @@ def test_tensor_core_nh32_train_path(cuda_model_factory):
         assert dn.max() <= 1e-2 and np.median(dn) <= 1e-3
         for k in KEYS:
             assert ge[k] < (5e-2 if k == "F" else 1e-2), k
+
+
+# ----------------------------------------------------------------------------- device dataloader feeding QFA.train
+def test_device_dataloader_on_gpu_and_train(tmp_path):
+    """DeviceDataloader on the GPU (delta through qfa_prepare_batch) == the same loader on the CPU (torch restatement of
+    dataloader.py:135-136), and QFA.train runs two epochs from it (model.py:183-231)."""
+    from qfa_b200 import QFA, Adam, step_scheduler, DeviceDataloader
+    from qfa_b200 import utils as U
+    wav, Nb, Nr = U.wavelength_grid(1030.0, 1600.0, 2e-3)
+    rng = np.random.default_rng(5)
+    n, P = 96, len(wav)
+    zq = rng.uniform(2.0, 3.5, n)
+    flux = rng.normal(1.0, 0.2, (n, P)); err = rng.uniform(0.05, 0.2, (n, P))
+    mask = rng.uniform(size=(n, P)) > 0.1
+    flux[~mask] = -999.0; err[~mask] = -999.0
+    lc = DeviceDataloader(flux, err, zq, mask, wav, batch_size=32, device="cpu", shuffle=False)
+    lg = DeviceDataloader(flux, err, zq, mask, wav, batch_size=32, device="cuda", shuffle=False)
+    assert relerr(lg.mu, lc.mu) < 1e-6
+    lc.rewind(); lg.rewind()
+    while lc.have_next_batch():
+        dc, ec, zc, mc = lc.next_batch()
+        dg, eg, zg, mg = lg.next_batch()
+        assert relerr(dg.cpu().numpy()[mc.numpy()], dc.numpy()[mc.numpy()]) < 2e-6
+        assert torch.equal(mg.cpu(), mc) and relerr(zg.cpu().numpy(), zc.numpy()) < 1e-6
+    assert not lg.have_next_batch()
+    torch.manual_seed(0)
+    m = QFA(Nb, Nr, 4, torch.device("cuda:0"), precision="fp32")
+    opt = Adam(params=m.parameters, device=torch.device("cuda:0"), scheduler=step_scheduler(0.9, 10), learning_rate=1e-3,
+               weight_decay=0.1)
+    m.train(opt, lg, 2, output_dir=str(tmp_path), save_interval=1, smooth_interval=5, quiet=True)
+    ck = np.load(os.path.join(str(tmp_path), "checkpoints", "model_parameters_epoch_02.npz"))
+    assert ck["F"].shape == (P, 4) and np.isfinite(ck["F"]).all() and relerr(ck["mu"], lc.mu) < 1e-6

@@ -206,3 +206,38 @@ def test_data_parallel_allreduce_gloo_world2():
     for rank, eF, et0, el, nsp in res:
         assert eF < 1e-12 and et0 < 1e-12 and el < 1e-12, (rank, eF, et0, el)
         assert nsp == 24.0
+
+
+# ----------------------------------------------------------------------------- device dataloader (host logic on CPU)
+def test_device_dataloader_matches_reference_formulas():
+    """zabs, mu and delta of qfa_b200.dataloader.DeviceDataloader against a NumPy restatement of reference
+    QFA/dataloader.py:102,110-112,135-136 and QFA/utils.py:206-219 (smooth)."""
+    from qfa_b200.dataloader import DeviceDataloader
+    wav, Nb, Nr = U.wavelength_grid(1030.0, 1600.0, 2e-3)
+    rng = np.random.default_rng(3)
+    n, P = 64, len(wav)
+    zq = rng.uniform(2.0, 3.5, n)
+    flux = rng.normal(1.0, 0.2, (n, P))
+    err = rng.uniform(0.05, 0.2, (n, P))
+    mask = rng.uniform(size=(n, P)) > 0.1
+    flux[~mask] = -999.0
+    ld = DeviceDataloader(flux, err, zq, mask, wav, batch_size=16, device="cpu", window_length_for_mu=16, shuffle=False)
+    # ---- NumPy restatement
+    zabs = (zq + 1).reshape(-1, 1) * wav[:Nb] / 1215.67 - 1                                   # dataloader.py:102
+    tau = 0.751 * ((1 + zabs) / 4.5) ** 2.90 - 0.132                                          # utils.py:105-106 (series 1)
+    s = np.hstack((np.exp(tau), np.ones((n, Nr))))
+    mu = np.sum(flux * s * mask, axis=0) / np.sum(flux != -999., axis=0)                      # dataloader.py:111
+    w = 16
+    sp = np.r_[mu[w - 1:0:-1], mu, mu[-2:-w - 1:-1]]                                          # utils.py:216-219
+    mu_s = np.convolve(np.ones(w) / w, sp, mode='valid')[int(w / 2 - 1):-int(w / 2)]
+    assert ld.mu.shape == (P,) and relerr(ld.mu, mu_s) < 1e-6
+    assert relerr(ld.zabs.numpy(), zabs) < 1e-6
+    ld.rewind()
+    d, e, z, m = ld.next_batch()
+    s_b = np.hstack((np.exp(-tau[:16]), np.ones((16, Nr))))
+    assert relerr(d.numpy(), flux[:16] - mu_s * s_b) < 1e-5                                   # dataloader.py:135-136
+    assert m.dtype == torch.bool and z.shape == (16, Nb) and e.shape == (16, P)
+    cnt = 16
+    while ld.have_next_batch():
+        cnt += ld.next_batch()[0].shape[0]
+    assert cnt == n
