@@ -345,6 +345,12 @@ def main():
         sys.exit(1)
     rank, world, local = dist_setup(args.gpus)
     torch.cuda.set_device(local)
+    if local == 0:
+        from qfa_b200 import _lib
+        _lib.build()                      # no-op when libqfa_b200.so is up to date
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
     peaks = {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)", "tf32_tflops": 1590.0 / 2,
              "tf32_source": "half of the fallback bf16 peak (B200_PROFILING.md)"}
     pj = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -14,6 +14,10 @@ CASES = ("sdss", "l32", "tiny5", "tiny12", "tiny3k", "tiny8m", "tiny16", "tiny1"
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the in-tree library is git-ignored: (re)build it when it is missing or older than its sources (nvcc cross-compiles
+    # sm_100a without a GPU; a fresh build takes ~1 minute, an up-to-date one is a no-op)
+    from qfa_b200 import _lib
+    _lib.build()
 
 
 def load_case(name, tag=None):
