@@ -351,7 +351,7 @@ constexpr int SOLVE32_LD = H32 + 1;
 constexpr int SOLVE32_WARP_DOUBLES = 2 * H32 * SOLVE32_LD + 2 * H32 + 8;      // M / M^-1, L^-1, b, a
 constexpr int SOLVE32_SMEM = SOLVE32_WARPS * SOLVE32_WARP_DOUBLES * 8;        // 17.4 KB per warp -> 12 warps per SM
 
-__global__ void __launch_bounds__(SOLVE32_WARPS * 32) k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img,
+__global__ void __launch_bounds__(SOLVE32_WARPS * 32, 3) k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img,
                                                                 float* __restrict__ nll, float* __restrict__ hasblue) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -364,38 +364,35 @@ __global__ void __launch_bounds__(SOLVE32_WARPS * 32) k_solve32(const float* __r
     for (int b = blockIdx.x * SOLVE32_WARPS + w; b < B; b += gridDim.x * SOLVE32_WARPS) {
         const float* src = gram + (size_t)b * G32_STRIDE;
         float* dst = img + (size_t)b * (G32_IMG / 4);
-        // lane <-> column l: rows k <= l of the packed upper triangle
-        for (int k = 0; k < H32; ++k) {
-            if (lane >= k) {
-                const double m = (double)__ldg(src + G32_M + tri32(k, lane)) + (k == lane ? 1.0 : 0.0);      // M = I + Gram
-                sM[k * LD + lane] = m;  sM[lane * LD + k] = m;
+        // ---- row `lane` of M = I + Gram in registers (the scratch holds the packed upper triangle), then a right-looking
+        //      Cholesky entirely in registers: pivots and columns travel by warp shuffles (no shared-memory round trips, no
+        //      lane-serial inner loop); afterwards a[k] (k <= lane) = L[lane][k], stored to sM for the triangular solves
+        {
+            double a[H32];
+#pragma unroll
+            for (int k = 0; k < H32; ++k) {
+                const int lo = k < lane ? k : lane, hi = k < lane ? lane : k;
+                a[k] = (double)__ldg(src + G32_M + tri32(lo, hi)) + (k == lane ? 1.0 : 0.0);
             }
+#pragma unroll
+            for (int j = 0; j < H32; ++j) {
+                const double djj = __shfl_sync(0xffffffffu, a[j], j);       // pivot, already reduced by the previous steps
+                const double inv = rsqrt(djj);
+                a[j] = (lane == j) ? djj * inv : a[j] * inv;                // column j of L (rows >= j)
+#pragma unroll
+                for (int k = j + 1; k < H32; ++k) {
+                    const double lkj = __shfl_sync(0xffffffffu, a[j], k);   // L[k][j]
+                    a[k] = fma(-a[j], lkj, a[k]);                           // rows < k hold junk there (never read)
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < H32; ++k) sM[lane * LD + k] = a[k];
         }
         sb[lane] = (double)__ldg(src + G32_B + lane);
-        // column `lane` of M2 (symmetric) straight into registers
-        double m2c[H32];
-#pragma unroll
-        for (int k = 0; k < H32; ++k) {
-            const int lo = k < lane ? k : lane, hi = k < lane ? lane : k;
-            m2c[k] = (double)__ldg(src + G32_M2 + tri32(lo, hi));
-        }
         __syncwarp();
-        // ---- right-looking Cholesky, lane <-> row
         double logdet = 0.0;
-        for (int j = 0; j < H32; ++j) {
-            const double d = sqrt(sM[j * LD + j]);
-            logdet += log(d);
-            const double inv = 1.0 / d;
-            __syncwarp();
-            if (lane == j) sM[j * LD + j] = d;
-            if (lane > j) sM[lane * LD + j] *= inv;
-            __syncwarp();
-            if (lane > j) {
-                const double lij = sM[lane * LD + j];
-                for (int k = j + 1; k <= lane; ++k) sM[lane * LD + k] -= lij * sM[k * LD + j];
-            }
-            __syncwarp();
-        }
+#pragma unroll
+        for (int j = 0; j < H32; ++j) logdet += log(sM[j * LD + j]);
         logdet *= 2.0;
         // ---- column `lane` of L^-1 in registers; image rows 32..63 (row n, K index = lane) come straight from them
         double x[H32];
@@ -412,7 +409,11 @@ __global__ void __launch_bounds__(SOLVE32_WARPS * 32) k_solve32(const float* __r
             dst[sw128_offset(H32 + r, lane) / 4] = tf32_rna((float)x[r]);
         }
         __syncwarp();
-        {                                                    // M^-1 = L^-T L^-1, lane <-> column
+        // ---- M^-1 = L^-T L^-1, lane <-> column (= row, symmetric): a = M^-1 b and b^T M^-1 b straight from the registers
+        //      (double); M^-1 itself goes to shared memory as FLOAT (rows of 36) for the product K = M^-1 M2
+        float* sMf = reinterpret_cast<float*>(sM);
+        double av = 0.0;
+        {
             double col[H32];
 #pragma unroll
             for (int r = 0; r < H32; ++r) {
@@ -422,31 +423,43 @@ __global__ void __launch_bounds__(SOLVE32_WARPS * 32) k_solve32(const float* __r
                 col[r] = sacc;
             }
 #pragma unroll
-            for (int r = 0; r < H32; ++r) sM[r * LD + lane] = col[r];
+            for (int r = 0; r < H32; ++r) av += col[r] * sb[r];                 // a_lane = sum_r Minv[lane][r] b_r
+            __syncwarp();                                                        // every lane is done reading sM (as L)
+#pragma unroll
+            for (int r = 0; r < H32; ++r) sMf[r * 36 + lane] = (float)col[r];
         }
-        __syncwarp();
-        double av = 0.0;
-        for (int k = 0; k < H32; ++k) av += sM[lane * LD + k] * sb[k];                 // a = M^-1 b
         sa[lane] = av;
         double quad = av * sb[lane];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) quad += __shfl_xor_sync(0xffffffffu, quad, o);
         dst[sw128_offset(2 * H32, lane) / 4] = tf32_rna((float)av);
         __syncwarp();
-        {                                                    // c = b2 - M2 a  (M2 symmetric: row `lane` = column `lane`)
-            double cv = (double)__ldg(src + G32_B2 + lane);
+        // column `lane` of M2 (symmetric) straight into registers.  M2 only enters well-conditioned PRODUCTS (K = M^-1 M2,
+        // c = b2 - M2 a) whose results are rounded to TF32: float is enough and halves the registers / issue slots
+        float m2c[H32];
 #pragma unroll
-            for (int k = 0; k < H32; ++k) cv -= m2c[k] * sa[k];
-            dst[sw128_offset(2 * H32 + 1, lane) / 4] = tf32_rna((float)cv);
+        for (int k = 0; k < H32; ++k) {
+            const int lo = k < lane ? k : lane, hi = k < lane ? lane : k;
+            m2c[k] = __ldg(src + G32_M2 + tri32(lo, hi));
         }
-        // ---- K = M^-1 M2, column `lane`; image rows 0..31: B[n][k] = K[k][n] -> row n = lane's column, K index = k
-        //      i.e. this lane writes K[r][lane] to image row `lane`, position r
+        {                                                    // c = b2 - M2 a  (M2 symmetric: row `lane` = column `lane`)
+            float cv = __ldg(src + G32_B2 + lane);
+#pragma unroll
+            for (int k = 0; k < H32; ++k) cv = fmaf(-m2c[k], (float)sa[k], cv);
+            dst[sw128_offset(2 * H32 + 1, lane) / 4] = tf32_rna(cv);
+        }
+        // ---- K = M^-1 M2, column `lane` (float); image rows 0..31: B[n][k] = K[k][n] -> this lane writes K[r][lane] to image
+        //      row `lane`, position r
 #pragma unroll
         for (int r = 0; r < H32; ++r) {
-            double sacc = 0.0;
+            float sacc = 0.f;
 #pragma unroll
-            for (int k = 0; k < H32; ++k) sacc += sM[r * LD + k] * m2c[k];
-            dst[sw128_offset(lane, r) / 4] = tf32_rna((float)sacc);
+            for (int k4 = 0; k4 < H32; k4 += 4) {
+                const float4 mv = *reinterpret_cast<const float4*>(sMf + r * 36 + k4);      // broadcast read
+                sacc = fmaf(mv.x, m2c[k4], sacc); sacc = fmaf(mv.y, m2c[k4 + 1], sacc);
+                sacc = fmaf(mv.z, m2c[k4 + 2], sacc); sacc = fmaf(mv.w, m2c[k4 + 3], sacc);
+            }
+            dst[sw128_offset(lane, r) / 4] = tf32_rna(sacc);
         }
         for (int n = 2 * H32 + 2; n < G32_ROWS; ++n) dst[sw128_offset(n, lane) / 4] = 0.0f;
         if (lane == 0) {
