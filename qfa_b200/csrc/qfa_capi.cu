@@ -457,7 +457,7 @@ static int train_accumulate_tc32(const QfaModel* m, const float* delta, const fl
     }
     Field<float> f = make_field<float>(m, delta, error, zabs, mask);
     TcGram32Args a;
-    a.f = f; a.B = B; a.ts = pl.ts; a.ntiles = pl.ntiles; a.nkb = pl.nkb; a.PB = PB; a.gram = gram;
+    a.f = f; a.B = B; a.ts = pl.ts; a.ntiles = pl.ntiles; a.nkb = pl.nkb; a.PB = PB; a.gram = gram; a.trace = g_trace;
     int grid = pl.ntiles < num_sms() ? pl.ntiles : num_sms();
     k_tc_gram32<<<grid, tcg::NTHREADS, SMEM32_BYTES, st>>>(a);
     CK(cudaGetLastError());

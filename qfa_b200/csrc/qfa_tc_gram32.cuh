@@ -99,12 +99,12 @@ __device__ __forceinline__ void compute_row32(const PhysConst& pc, const PixCons
     const float A2 = A * A;
     const float D = fmaf(A2, px.psi, fmaf(rb.e, rb.e, oz));                         // model.py:128-131
     const float w = rcpf(D);
-    const float r = rb.x;
     const float wA = w * A;
     const float s2 = wA * A;
     sts_f32_imm<0>(sa, mk ? tf32_round(s2) : 0.0f);
     if (BLUE != 0) sts_f32_imm<2 * A_TILE>(sa, mk ? tf32_round(s2 * A) : 0.0f);     // s3 (= s2 on red K-blocks)
     if (PASS0) {
+        const float r = rb.x;
         const float wb = wA * r;
         sts_f32_imm<A_TILE>(sa, mk ? tf32_round(wb) : 0.0f);
         if (BLUE != 0) {
@@ -133,6 +133,7 @@ struct TcGram32Args {
     int ntiles, nkb;
     const float* PB;       // [nkb][PB32_KB_BYTES/4]
     float* gram;           // [B][G32_STRIDE]
+    long long* trace;      // debug (-DQFA_ENABLE_TRACE): CTA 0, first tile: [pass][kb][warp][4] clock64 stamps
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g) {
@@ -248,8 +249,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                     constexpr bool PASS0 = decltype(p0_tag)::value;
                     auto load_kb = [&](int kb, KBuf& k) {
                         const int p0 = kb * KB;
-                        if (p0 + KB <= P) load_kblock<true, true, NR>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
-                        else load_kblock<true, false, NR>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
+                        // passes 1, 2 generate s2 / s3 only: they do not depend on delta, so it is not even loaded
+                        if (p0 + KB <= P) load_kblock<true, true, NR, PASS0>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
+                        else load_kblock<true, false, NR, PASS0>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
                     };
                     load_kb(0, kA);
                     if (nkb > 1) load_kb(1, kB);
@@ -259,16 +261,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                         const uint32_t u = git / NSTAGE32;
                         const int p0 = kb * KB;
                         const bool blue = p0 + lane < Nb;
+                        long long* tr = (kTrace && g.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && lane == 0)
+                                            ? g.trace + (((size_t)pass * nkb + kb) * NPW + warp) * 4 : nullptr;
+                        if (tr) tr[0] = clock64();
                         if (u > 0) mbar_wait_or_trap(&bar_empty[s], (u - 1) & 1);
+                        if (tr) tr[1] = clock64();
                         const uint32_t stage_sa = ring_sa + (uint32_t)s * (uint32_t)STAGE32_BYTES;
                         const int bm = (p0 + KB <= Nb) ? 1 : (p0 >= Nb ? 0 : 2);
                         if (bm == 1) kblock_consume32<1, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
                         else if (bm == 0) kblock_consume32<0, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
                         else kblock_consume32<2, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
+                        if (tr) tr[2] = clock64();
                         fence_proxy_async();            // MEMBAR.ALL.CTA: before the prefetch below, never after it
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bar_full[s]);
                         if (kb + 2 < nkb) load_kb(kb + 2, k);
+                        if (tr) tr[3] = clock64();
                     };
                     for (int kb = 0; kb < nkb; kb += 2) {
                         do_kblock(kb, kA);
