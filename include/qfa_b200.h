@@ -50,6 +50,8 @@ extern "C" {
 #define QFA_FLAG_ZERO_ACC 1     /* qfa_train_accumulate: clear `acc` before accumulating */
 #define QFA_FLAG_FORCE_TENSOR 2 /* QFA_PREC_TF32: use the tcgen05 kernels even for batches smaller than
                                    QFA_TC_MIN_BATCH (env, default 1024) spectra */
+#define QFA_FLAG_SOLVE_FP64 4   /* QFA_PREC_TF32, 8 < Nh <= 32: per-spectrum Cholesky in double instead of float (7 % slower
+                                   train step; no measurable difference on any parity case, kept for ill-conditioned models) */
 
 /* error codes (negative) */
 #define QFA_ERR_NULL -1

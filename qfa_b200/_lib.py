@@ -24,6 +24,7 @@ PRECISIONS = {"fp64": PREC_FP64, "fp32": PREC_FP32, "mixed": PREC_TF32, "tf32": 
 TAU_LAWS = {"becker": 0, "fg": 1, "kamble": 2, "mock": 3}
 FLAG_ZERO_ACC = 1
 FLAG_FORCE_TENSOR = 2
+FLAG_SOLVE_FP64 = 4
 
 
 class QfaError(RuntimeError):
@@ -49,6 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     extra = ["-DQFA_ENABLE_TRACE"] if os.environ.get("QFA_ENABLE_TRACE") else []     # clock64 stamps for scratch/*_trace.py
+    extra += os.environ.get("QFA_NVCC_EXTRA", "").split()                            # A/B variants (scratch/run_variants.sh)
     cmd = [nvcc] + NVCC_FLAGS + extra + SOURCES + ["-o", LIB_PATH + ".tmp"]
     if verbose:
         print(" ".join(cmd))

@@ -451,7 +451,8 @@ static int train_accumulate_tc32(const QfaModel* m, const float* delta, const fl
     static bool attr_done = false;
     if (!attr_done) {
         CK(cudaFuncSetAttribute(k_tc_gram32, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM32_BYTES));
-        CK(cudaFuncSetAttribute(k_solve32, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE32_SMEM));
+        CK(cudaFuncSetAttribute(k_solve32<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE32_SMEM));
+        CK(cudaFuncSetAttribute(k_solve32<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE32_SMEM));
         CK(cudaFuncSetAttribute(k_tc_grad32, cudaFuncAttributeMaxDynamicSharedMemorySize, G32_SMEM));
         attr_done = true;
     }
@@ -462,8 +463,9 @@ static int train_accumulate_tc32(const QfaModel* m, const float* delta, const fl
     k_tc_gram32<<<grid, tcg::NTHREADS, SMEM32_BYTES, st>>>(a);
     CK(cudaGetLastError());
     int sblocks = (B + SOLVE32_WARPS - 1) / SOLVE32_WARPS;
-    if (sblocks > 3 * num_sms()) sblocks = 3 * num_sms();        // 3 CTAs (12 warps) per SM fit
-    k_solve32<<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, small, nll, hasblue);
+    if (sblocks > QFA_SOLVE32_CTAS * num_sms()) sblocks = QFA_SOLVE32_CTAS * num_sms();
+    if (flags & QFA_FLAG_SOLVE_FP64) k_solve32<double><<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, small, nll, hasblue);
+    else k_solve32<float><<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, small, nll, hasblue);
     CK(cudaGetLastError());
     TcGrad32Args gr;
     gr.f = f; gr.B = B; gr.nsplit = pl.nsplit; gr.img = small; gr.part = part; gr.spart = spart;

@@ -44,6 +44,10 @@ constexpr int G32_STRIDE = 1124;
 // ---- k_tc_grad32 / k_solve32 image geometry
 constexpr int G32_ROWS = 80;                          // image rows per spectrum (UMMA N)
 constexpr int G32_IMG = G32_ROWS * 128;               // 10 240 B
+#ifndef QFA_G32_LIVE_ROWS
+#define QFA_G32_LIVE_ROWS (2 * H32 + 2)
+#endif
+constexpr int G32_LIVE = QFA_G32_LIVE_ROWS * 128;         // rows 0..65 carry data (8 448 B): only these are written and copied
 constexpr int G32_SPS = 3;                            // spectra per step
 constexpr int G32_STAGE = G32_SPS * G32_IMG;          // 30 720 B
 constexpr int G32_NST = 4;                            // image ring stages
@@ -355,124 +359,181 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
 // [a | c | L^-1 | K] (SmallLayout<32>, float) that k_grad<float,32> consumes.           (model.py:132-135, utils.py:29-54)
 // ---------------------------------------------------------------------------------------
 constexpr int SOLVE32_WARPS = 4;
-constexpr int SOLVE32_LD = H32 + 1;
-constexpr int SOLVE32_WARP_DOUBLES = 2 * H32 * SOLVE32_LD + 2 * H32 + 8;      // M / M^-1, L^-1, b, a
-constexpr int SOLVE32_SMEM = SOLVE32_WARPS * SOLVE32_WARP_DOUBLES * 8;        // 17.4 KB per warp -> 12 warps per SM
+constexpr int SOLVE32_LD = 36;                                                  // float rows of 36: 16-byte aligned, LDS.128
+constexpr int SOLVE32_WARP_FLOATS = 2 * H32 * SOLVE32_LD + 4 * H32;             // L -> L^-T, L^-1, b, y, a, spare
+constexpr int SOLVE32_SMEM = SOLVE32_WARPS * SOLVE32_WARP_FLOATS * 4;           // 9.5 KB per warp
+#ifndef QFA_SOLVE32_CTAS
+#define QFA_SOLVE32_CTAS 4
+#endif
 
-__global__ void __launch_bounds__(SOLVE32_WARPS * 32, 3) k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img,
-                                                                float* __restrict__ nll, float* __restrict__ hasblue) {
+__device__ __forceinline__ float solve32_rsqrt(float x) {
+    const float y = rsqrtf(x);
+    return y * fmaf(-0.5f * x * y, y, 1.5f);             // one Newton step: full float accuracy
+}
+__device__ __forceinline__ double solve32_rsqrt(double x) { return rsqrt(x); }
+
+// Everything after the factorisation is float and uses the TRIANGULAR factors only: y = L^-1 b, a = L^-T y,
+// b^T M^-1 b = |y|^2, K = L^-T (L^-1 M2).  Each step then loses eps x cond(L) = eps x sqrt(cond(M)), where forming M^-1
+// first and multiplying (eps x cond(M), cond(M) up to ~1e6 for high signal-to-noise spectra) would not do in float.
+// TC = scalar type of the Cholesky factorisation itself: float by default (identical parity figures on every test case,
+// including the badly conditioned 96-pixel ones; 7 % faster step), double with QFA_FLAG_SOLVE_FP64.
+template <typename TC>
+__global__ void __launch_bounds__(SOLVE32_WARPS * 32, QFA_SOLVE32_CTAS)
+k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float* __restrict__ nll, float* __restrict__ hasblue) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double* base = reinterpret_cast<double*>(smem_raw) + (size_t)w * SOLVE32_WARP_DOUBLES;
-    double* sM = base;                              // M -> L -> M^-1
-    double* sL = sM + H32 * SOLVE32_LD;             // L^-1 (lower)
-    double* sb = sL + H32 * SOLVE32_LD;
-    double* sa = sb + H32;
     constexpr int LD = SOLVE32_LD;
+    float* sA = reinterpret_cast<float*>(smem_raw) + (size_t)w * SOLVE32_WARP_FLOATS;   // rows of L (diagonal = 1/L_jj), then L^-T
+    float* sLi = sA + H32 * LD;                     // L^-1, row-major
+    float* sb = sLi + H32 * LD;
+    float* sy = sb + H32;
+    float* sa = sy + H32;
     for (int b = blockIdx.x * SOLVE32_WARPS + w; b < B; b += gridDim.x * SOLVE32_WARPS) {
         const float* src = gram + (size_t)b * G32_STRIDE;
         float* dst = img + (size_t)b * (G32_IMG / 4);
         // ---- row `lane` of M = I + Gram in registers (the scratch holds the packed upper triangle), then a right-looking
         //      Cholesky entirely in registers: pivots and columns travel by warp shuffles (no shared-memory round trips, no
-        //      lane-serial inner loop); afterwards a[k] (k <= lane) = L[lane][k], stored to sM for the triangular solves
+        //      lane-serial inner loop); afterwards a[k] (k <= lane) = L[lane][k]
+        float logdet;
         {
-            double a[H32];
+            TC a[H32];
 #pragma unroll
             for (int k = 0; k < H32; ++k) {
                 const int lo = k < lane ? k : lane, hi = k < lane ? lane : k;
-                a[k] = (double)__ldg(src + G32_M + tri32(lo, hi)) + (k == lane ? 1.0 : 0.0);
+                a[k] = (TC)__ldg(src + G32_M + tri32(lo, hi)) + (k == lane ? TC(1) : TC(0));
             }
+            sb[lane] = __ldg(src + G32_B + lane);
+            TC myinv = TC(1), mydiag = TC(1);
 #pragma unroll
             for (int j = 0; j < H32; ++j) {
-                const double djj = __shfl_sync(0xffffffffu, a[j], j);       // pivot, already reduced by the previous steps
-                const double inv = rsqrt(djj);
-                a[j] = (lane == j) ? djj * inv : a[j] * inv;                // column j of L (rows >= j)
+                const TC djj = __shfl_sync(0xffffffffu, a[j], j);           // pivot, already reduced by the previous steps
+                const TC inv = solve32_rsqrt(djj);
+                if (lane == j) { myinv = inv; mydiag = djj; }
+                a[j] *= inv;                                                // column j of L (rows >= j)
 #pragma unroll
                 for (int k = j + 1; k < H32; ++k) {
-                    const double lkj = __shfl_sync(0xffffffffu, a[j], k);   // L[k][j]
+                    const TC lkj = __shfl_sync(0xffffffffu, a[j], k);       // L[k][j]
                     a[k] = fma(-a[j], lkj, a[k]);                           // rows < k hold junk there (never read)
                 }
             }
 #pragma unroll
-            for (int k = 0; k < H32; ++k) sM[lane * LD + k] = a[k];
-        }
-        sb[lane] = (double)__ldg(src + G32_B + lane);
-        __syncwarp();
-        double logdet = 0.0;
-#pragma unroll
-        for (int j = 0; j < H32; ++j) logdet += log(sM[j * LD + j]);
-        logdet *= 2.0;
-        // ---- column `lane` of L^-1 in registers; image rows 32..63 (row n, K index = lane) come straight from them
-        double x[H32];
-#pragma unroll
-        for (int r = 0; r < H32; ++r) {
-            double sacc = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
-            for (int k = 0; k < r; ++k) sacc -= sM[r * LD + k] * x[k];
-            x[r] = sacc / sM[r * LD + r];
-        }
-#pragma unroll
-        for (int r = 0; r < H32; ++r) {
-            sL[r * LD + lane] = x[r];
-            dst[sw128_offset(H32 + r, lane) / 4] = tf32_rna((float)x[r]);
-        }
-        __syncwarp();
-        // ---- M^-1 = L^-T L^-1, lane <-> column (= row, symmetric): a = M^-1 b and b^T M^-1 b straight from the registers
-        //      (double); M^-1 itself goes to shared memory as FLOAT (rows of 36) for the product K = M^-1 M2
-        float* sMf = reinterpret_cast<float*>(sM);
-        double av = 0.0;
-        {
-            double col[H32];
-#pragma unroll
-            for (int r = 0; r < H32; ++r) {
-                double sacc = 0.0;
-#pragma unroll
-                for (int k = r; k < H32; ++k) sacc += sL[k * LD + r] * x[k];
-                col[r] = sacc;
+            for (int k4 = 0; k4 < H32; k4 += 4) {
+                float4 v;
+                v.x = (k4 == lane) ? (float)myinv : (float)a[k4];
+                v.y = (k4 + 1 == lane) ? (float)myinv : (float)a[k4 + 1];
+                v.z = (k4 + 2 == lane) ? (float)myinv : (float)a[k4 + 2];
+                v.w = (k4 + 3 == lane) ? (float)myinv : (float)a[k4 + 3];
+                *reinterpret_cast<float4*>(sA + lane * LD + k4) = v;
             }
+            logdet = logf((float)mydiag);                                   // log det M = sum_j log(pivot_j): one log per lane
 #pragma unroll
-            for (int r = 0; r < H32; ++r) av += col[r] * sb[r];                 // a_lane = sum_r Minv[lane][r] b_r
-            __syncwarp();                                                        // every lane is done reading sM (as L)
-#pragma unroll
-            for (int r = 0; r < H32; ++r) sMf[r * 36 + lane] = (float)col[r];
+            for (int o = 16; o > 0; o >>= 1) logdet += __shfl_xor_sync(0xffffffffu, logdet, o);
         }
-        sa[lane] = av;
-        double quad = av * sb[lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) quad += __shfl_xor_sync(0xffffffffu, quad, o);
-        dst[sw128_offset(2 * H32, lane) / 4] = tf32_rna((float)av);
-        __syncwarp();
-        // column `lane` of M2 (symmetric) straight into registers.  M2 only enters well-conditioned PRODUCTS (K = M^-1 M2,
-        // c = b2 - M2 a) whose results are rounded to TF32: float is enough and halves the registers / issue slots
+        // column `lane` of M2 (symmetric): issued here so that the scattered loads fly under the substitution
         float m2c[H32];
 #pragma unroll
         for (int k = 0; k < H32; ++k) {
             const int lo = k < lane ? k : lane, hi = k < lane ? lane : k;
             m2c[k] = __ldg(src + G32_M2 + tri32(lo, hi));
         }
-        {                                                    // c = b2 - M2 a  (M2 symmetric: row `lane` = column `lane`)
-            float cv = __ldg(src + G32_B2 + lane);
+        float cv = __ldg(src + G32_B2 + lane);
+        __syncwarp();
+        // ---- column `lane` of L^-1 in registers (forward substitution, rows of L broadcast from shared memory)
+        float x[H32];
 #pragma unroll
-            for (int k = 0; k < H32; ++k) cv = fmaf(-m2c[k], (float)sa[k], cv);
-            dst[sw128_offset(2 * H32 + 1, lane) / 4] = tf32_rna(cv);
+        for (int r = 0; r < H32; ++r) {
+            float sacc = (r == lane) ? 1.f : 0.f;
+            float dinv = 0.f;
+#pragma unroll
+            for (int k4 = 0; k4 <= r; k4 += 4) {
+                const float4 lv = *reinterpret_cast<const float4*>(sA + r * LD + k4);
+                if (k4 < r) sacc = fmaf(-lv.x, x[k4], sacc); else if (k4 == r) dinv = lv.x;
+                if (k4 + 1 < r) sacc = fmaf(-lv.y, x[k4 + 1], sacc); else if (k4 + 1 == r) dinv = lv.y;
+                if (k4 + 2 < r) sacc = fmaf(-lv.z, x[k4 + 2], sacc); else if (k4 + 2 == r) dinv = lv.z;
+                if (k4 + 3 < r) sacc = fmaf(-lv.w, x[k4 + 3], sacc); else if (k4 + 3 == r) dinv = lv.w;
+            }
+            x[r] = sacc * dinv;
         }
-        // ---- K = M^-1 M2, column `lane` (float); image rows 0..31: B[n][k] = K[k][n] -> this lane writes K[r][lane] to image
-        //      row `lane`, position r
+        // image rows 32..63 (row n, K index = lane) straight from the registers; L^-1 row-major and (over L) transposed
+#pragma unroll
+        for (int r = 0; r < H32; ++r) {
+            sLi[r * LD + lane] = x[r];
+            dst[sw128_offset(H32 + r, lane) / 4] = tf32_rna(x[r]);
+        }
+        __syncwarp();                                                        // every lane is done reading sA (as L)
+#pragma unroll
+        for (int r4 = 0; r4 < H32; r4 += 4)
+            *reinterpret_cast<float4*>(sA + lane * LD + r4) = make_float4(x[r4], x[r4 + 1], x[r4 + 2], x[r4 + 3]);
+        // ---- y = L^-1 b (lane = row), quad = |y|^2 = b^T M^-1 b
+        float y = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < H32; c4 += 4) {
+            const float4 lv = *reinterpret_cast<const float4*>(sLi + lane * LD + c4);
+            const float4 bv = *reinterpret_cast<const float4*>(sb + c4);
+            y = fmaf(lv.x, bv.x, y); y = fmaf(lv.y, bv.y, y); y = fmaf(lv.z, bv.z, y); y = fmaf(lv.w, bv.w, y);
+        }
+        sy[lane] = y;
+        float quad = y * y;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) quad += __shfl_xor_sync(0xffffffffu, quad, o);
+        __syncwarp();
+        // ---- a = L^-T y (lane = column of L^-1, in registers)
+        float av = 0.f;
+#pragma unroll
+        for (int r4 = 0; r4 < H32; r4 += 4) {
+            const float4 yv = *reinterpret_cast<const float4*>(sy + r4);
+            av = fmaf(x[r4], yv.x, av); av = fmaf(x[r4 + 1], yv.y, av); av = fmaf(x[r4 + 2], yv.z, av); av = fmaf(x[r4 + 3], yv.w, av);
+        }
+        sa[lane] = av;
+        dst[sw128_offset(2 * H32, lane) / 4] = tf32_rna(av);
+        __syncwarp();
+        // ---- c = b2 - M2 a  (M2 symmetric: row `lane` = column `lane`)
+#pragma unroll
+        for (int k4 = 0; k4 < H32; k4 += 4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(sa + k4);
+            cv = fmaf(-m2c[k4], a4.x, cv); cv = fmaf(-m2c[k4 + 1], a4.y, cv);
+            cv = fmaf(-m2c[k4 + 2], a4.z, cv); cv = fmaf(-m2c[k4 + 3], a4.w, cv);
+        }
+        dst[sw128_offset(2 * H32 + 1, lane) / 4] = tf32_rna(cv);
+        // ---- W = L^-1 M2, column `lane`:  W[r] = sum_{c <= r} Linv[r][c] M2[c][lane]   (rows of L^-1 broadcast)
+        float wv[H32];
 #pragma unroll
         for (int r = 0; r < H32; ++r) {
             float sacc = 0.f;
 #pragma unroll
-            for (int k4 = 0; k4 < H32; k4 += 4) {
-                const float4 mv = *reinterpret_cast<const float4*>(sMf + r * 36 + k4);      // broadcast read
-                sacc = fmaf(mv.x, m2c[k4], sacc); sacc = fmaf(mv.y, m2c[k4 + 1], sacc);
-                sacc = fmaf(mv.z, m2c[k4 + 2], sacc); sacc = fmaf(mv.w, m2c[k4 + 3], sacc);
+            for (int c4 = 0; c4 <= r; c4 += 4) {
+                const float4 lv = *reinterpret_cast<const float4*>(sLi + r * LD + c4);
+                sacc = fmaf(lv.x, m2c[c4], sacc);
+                if (c4 + 1 <= r) sacc = fmaf(lv.y, m2c[c4 + 1], sacc);
+                if (c4 + 2 <= r) sacc = fmaf(lv.z, m2c[c4 + 2], sacc);
+                if (c4 + 3 <= r) sacc = fmaf(lv.w, m2c[c4 + 3], sacc);
             }
-            dst[sw128_offset(lane, r) / 4] = tf32_rna(sacc);
+            wv[r] = sacc;
         }
-        for (int n = 2 * H32 + 2; n < G32_ROWS; ++n) dst[sw128_offset(n, lane) / 4] = 0.0f;
+        // ---- K = L^-T W, column `lane`:  K[k] = sum_{r >= k} Linv[r][k] W[r]   (rows of L^-T broadcast).  Image rows 0..31:
+        //      B[n][k] = K[k][n] -> this lane owns image row `lane`, four consecutive k per 16-byte store
+#pragma unroll
+        for (int k4 = 0; k4 < H32; k4 += 4) {
+            float kk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = k4 + q;
+                float sacc = 0.f;
+#pragma unroll
+                for (int r4 = k4; r4 < H32; r4 += 4) {
+                    const float4 lv = *reinterpret_cast<const float4*>(sA + k * LD + r4);
+                    if (r4 >= k) sacc = fmaf(lv.x, wv[r4], sacc);
+                    if (r4 + 1 >= k) sacc = fmaf(lv.y, wv[r4 + 1], sacc);
+                    if (r4 + 2 >= k) sacc = fmaf(lv.z, wv[r4 + 2], sacc);
+                    sacc = fmaf(lv.w, wv[r4 + 3], sacc);
+                }
+                kk[q] = tf32_rna(sacc);
+            }
+            *reinterpret_cast<float4*>(dst + sw128_offset(lane, k4) / 4) = make_float4(kk[0], kk[1], kk[2], kk[3]);
+        }
         if (lane == 0) {
             const double E = (double)__ldg(src + G32_E);
-            nll[b] = (float)(0.5 * (E - quad + logdet));                                       // model.py:135
+            nll[b] = (float)(0.5 * (E - (double)quad + (double)logdet));                       // model.py:135
             hasblue[b] = __ldg(src + G32_E + 1);
         }
         __syncwarp();
@@ -540,8 +601,13 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
             }
             sts_v4(smem_u32(sm) + G32_A_OFF + sw128_offset(pi, c4 * 4), v[0], v[1], v[2], v[3]);
         }
-        fence_proxy_async();
     }
+    // rows 66..79 of every ring image are zero and stay zero: the bulk copies only bring the 66 live rows
+    for (int q = tid; q < G32_NST * G32_SPS * ((G32_IMG - G32_LIVE) / 16); q += G32_THREADS) {
+        const int im = q / ((G32_IMG - G32_LIVE) / 16), o = q % ((G32_IMG - G32_LIVE) / 16);
+        sts_v4(smem_u32(sm) + G32_B_OFF + im * G32_IMG + G32_LIVE + o * 16, 0.f, 0.f, 0.f, 0.f);
+    }
+    fence_proxy_async();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -561,8 +627,10 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
             auto issue_b = [&](int n) {           // images of step n -> ring stage n % 4
                 const int s = n % G32_NST;
                 const size_t b0 = (size_t)(st0 + n) * G32_SPS;
-                mbar_expect_tx(&bar_b[s], G32_STAGE);
-                bulk_g2s(sm + G32_B_OFF + s * G32_STAGE, g.img + b0 * (G32_IMG / 4), G32_STAGE, &bar_b[s]);
+                mbar_expect_tx(&bar_b[s], G32_SPS * G32_LIVE);
+#pragma unroll
+                for (int sp = 0; sp < G32_SPS; ++sp)
+                    bulk_g2s(sm + G32_B_OFF + s * G32_STAGE + sp * G32_IMG, g.img + (b0 + sp) * (G32_IMG / 4), G32_LIVE, &bar_b[s]);
             };
             for (int n = 0; n < 2 && n < nst; ++n) issue_b(n);
             const uint64_t dA = desc_sw128_kmajor(sm_sa + G32_A_OFF);

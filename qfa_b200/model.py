@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import QfaError, QfaModelStruct, PRECISIONS, FLAG_ZERO_ACC, FLAG_FORCE_TENSOR
+from ._lib import QfaError, QfaModelStruct, PRECISIONS, FLAG_ZERO_ACC, FLAG_FORCE_TENSOR, FLAG_SOLVE_FP64
 from .utils import default_tau, resolve_tau_law
 
 log2pi = 1.8378770664093453  # reference model.py:20
@@ -66,6 +66,7 @@ class QFA(object):
         self._loss = None
         self.process_group = None  # set by enable_data_parallel()
         self._dp = False
+        self.solve_fp64 = False    # mixed mode, 8 < Nh <= 32: per-spectrum Cholesky in double instead of float
         if model_params is not None:
             for k in _KEYS:
                 self._view(k).copy_(torch.as_tensor(np.asarray(model_params[k]), dtype=torch.float32))
@@ -159,7 +160,7 @@ class QFA(object):
 
     @property
     def _flags(self):
-        return FLAG_FORCE_TENSOR if self.precision == "tf32" else 0
+        return (FLAG_FORCE_TENSOR if self.precision == "tf32" else 0) | (FLAG_SOLVE_FP64 if self.solve_fp64 else 0)
 
     @property
     def _tdtype(self):

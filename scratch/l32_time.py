@@ -8,6 +8,8 @@ Bn = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 d = synth.make_spectra(P, mu, grid, Bn, seed=11, device=torch.device("cuda:0"), mask_iid=0.15, run_len=(40, 160))
 Pn = {k: v.numpy() for k, v in P.items()}
 m = QFA(grid.Nb, grid.Nr, 32, torch.device("cuda:0"), model_params=Pn, precision="tf32")
+import os
+m.solve_fp64 = bool(os.environ.get("QFA_SOLVE_FP64"))
 args = (d["delta"], d["error"], d["zabs"], d["mask"].view(torch.uint8))
 for _ in range(3): m.accumulate(*args)
 torch.cuda.synchronize()
