@@ -220,7 +220,7 @@ static TcTrainPlan plan_tc_train(int Nb, int Nr, int Nh, int B) {
 struct Tc32Plan {
     int nkb, ntiles, npix_tiles, nsplit, ntiles_blue;
     tcg::TileSched ts;
-    size_t off_pb, off_gram, off_small, off_hasblue, off_nll, off_part, off_spart, total;
+    size_t off_pb, off_gram, off_small, off_hasblue, off_nll, off_part, off_spart, off_replay, total;
 };
 static inline bool tc32_eligible(int Nh, int precision) { return precision == QFA_PREC_TF32 && Nh > tcg::HP && Nh <= 32; }   // zero-padded to 32
 static Tc32Plan plan_tc32(int Nb, int Nr, int Nh, int B) {
@@ -244,6 +244,10 @@ static Tc32Plan plan_tc32(int Nb, int Nr, int Nh, int B) {
     p.off_nll = o;     o = align_up(o + Bn * 4, 256);
     p.off_part = o;    o = align_up(o + (size_t)p.nsplit * part_len(P, Nb, Nh) * 4, 256);
     p.off_spart = o;   o = align_up(o + (size_t)p.nsplit * p.npix_tiles * 3 * 4, 256);
+    // k_tc_gram32 replay buffer: one tile's s2 / s3 operand tiles per CTA (independent of B; 1 MB per CTA at 1000 pixels)
+    const int gram_ctas = p.ntiles < num_sms() ? p.ntiles : num_sms();
+    p.off_replay = o = align_up(o, 1024);
+    o = align_up(o + (size_t)(gram_ctas > 0 ? gram_ctas : 1) * p.nkb * tcg32::RP_KB_FLOATS * 4, 1024);
     p.total = o;
     return p;
 }
@@ -459,6 +463,7 @@ static int train_accumulate_tc32(const QfaModel* m, const float* delta, const fl
     Field<float> f = make_field<float>(m, delta, error, zabs, mask);
     TcGram32Args a;
     a.f = f; a.B = B; a.ts = pl.ts; a.ntiles = pl.ntiles; a.nkb = pl.nkb; a.PB = PB; a.gram = gram; a.trace = g_trace;
+    a.replay = reinterpret_cast<float*>(ws + pl.off_replay);
     int grid = pl.ntiles < num_sms() ? pl.ntiles : num_sms();
     k_tc_gram32<<<grid, tcg::NTHREADS, SMEM32_BYTES, st>>>(a);
     CK(cudaGetLastError());
@@ -468,7 +473,7 @@ static int train_accumulate_tc32(const QfaModel* m, const float* delta, const fl
     else k_solve32<float><<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, small, nll, hasblue);
     CK(cudaGetLastError());
     TcGrad32Args gr;
-    gr.f = f; gr.B = B; gr.nsplit = pl.nsplit; gr.img = small; gr.part = part; gr.spart = spart;
+    gr.f = f; gr.B = B; gr.nsplit = pl.nsplit; gr.img = small; gr.part = part; gr.spart = spart; gr.trace = g_trace_grad;
     k_tc_grad32<<<dim3(pl.npix_tiles, pl.nsplit), G32_THREADS, G32_SMEM, st>>>(gr);
     CK(cudaGetLastError());
     ReduceArgs<float> ra;

@@ -35,6 +35,14 @@ constexpr int PB32_SLOT = (SLICE + H32) * 128;     // 32 KB: a slice of the prod
 constexpr int PB32_OFF = NSTAGE32 * STAGE32_BYTES;
 constexpr int SMEM32_BYTES = PB32_OFF + NPB32 * PB32_SLOT + 1024;
 constexpr int PB32_LEAD = NPB32 - NSTAGE32;
+// passes 1, 2 REPLAY the s2 / s3 operand tiles that pass 0 generated (stored pre-swizzled to a per-CTA global buffer, mostly
+// L2-resident) with bulk copies: no worker math at all.  The pass-0 ring is re-cut into RP_NST stages of [s2 | s3].
+constexpr int RP_NST = 4;
+constexpr int RP_LEAD = 3;
+constexpr int RP_STAGE = 2 * A_TILE;
+constexpr int RP_TILE = TSH * 128;                  // 120 live rows of a tile (15 360 B)
+constexpr int RP_KB_FLOATS = 2 * A_TILE / 4;        // replay buffer per K-block: [s2 tile | s3 tile]
+static_assert(RP_NST * RP_STAGE <= NSTAGE32 * STAGE32_BYTES, "replay stages live in the pass-0 ring");
 // TMEM columns (all 512): M slice | M2 slice | b | b2
 constexpr int T_A = 0, T_C = SLICE, T_B = 2 * SLICE, T_D = 2 * SLICE + H32;
 // scratch row per spectrum (floats): [M - I packed (528) | M2 packed (528) | b (32) | b2 (32) | E | n_blue>0 | pad]
@@ -47,16 +55,21 @@ constexpr int G32_IMG = G32_ROWS * 128;               // 10 240 B
 #ifndef QFA_G32_LIVE_ROWS
 #define QFA_G32_LIVE_ROWS (2 * H32 + 2)
 #endif
+#ifndef QFA_G32_CELL_LEAD
+#define QFA_G32_CELL_LEAD 4
+#endif
+constexpr int G32_CELL_LEAD = QFA_G32_CELL_LEAD;      // even (TMEM buffer parity is compile-time per unrolled step)
 constexpr int G32_LIVE = QFA_G32_LIVE_ROWS * 128;         // rows 0..65 carry data (8 448 B): only these are written and copied
 constexpr int G32_SPS = 3;                            // spectra per step
 constexpr int G32_STAGE = G32_SPS * G32_IMG;          // 30 720 B
-constexpr int G32_NST = 4;                            // image ring stages
+constexpr int G32_NST = 5;                            // image ring stages (see k_tc_grad32: copy of step n+2 overwrites step n-3)
 constexpr int G32_W = 12;                             // worker warps
 constexpr int G32_THREADS = (G32_W + 1) * 32;
 constexpr int G32_A_OFF = 0;                          // 16 KB: F rows of the pixel tile
 constexpr int G32_B_OFF = 16384;
-constexpr int G32_RED_OFF = G32_B_OFF + G32_NST * G32_STAGE;        // epilogue: [3 groups][128 pixels][40] floats
-constexpr int G32_SMEM = G32_RED_OFF + 3 * 128 * 40 * 4 + 1024;
+constexpr int G32_RED_OFF = G32_B_OFF;                // epilogue [3 groups][128 pixels][40] floats: over the (then idle) ring
+constexpr int G32_SMEM = G32_B_OFF + G32_NST * G32_STAGE + 1024;
+static_assert(3 * 128 * 40 * 4 <= G32_NST * G32_STAGE, "epilogue staging fits the ring");
 constexpr int G32_TBUF = 256;                         // TMEM columns per buffer (3 x 80 used)
 
 
@@ -88,7 +101,7 @@ __global__ void k_tc_build_images32(const float* __restrict__ F, int P, int Nh, 
 // per-cell physics + operand generation; PASS0 also produces the wb / wb2 operands and the scalar sums
 template <int BLUE, bool PASS0>
 __device__ __forceinline__ void compute_row32(const PhysConst& pc, const PixConst& px, const RowBuf& rb, bool blue, uint32_t sa,
-                                              float& E, uint32_t& nbm, int j) {
+                                              float& E, uint32_t& nbm, int j, float* __restrict__ rp) {
     const bool mk = rb.m != 0u;
     float A = 1.0f, oz = 0.0f;
     if (BLUE != 0) {
@@ -105,8 +118,14 @@ __device__ __forceinline__ void compute_row32(const PhysConst& pc, const PixCons
     const float w = rcpf(D);
     const float wA = w * A;
     const float s2 = wA * A;
-    sts_f32_imm<0>(sa, mk ? tf32_round(s2) : 0.0f);
-    if (BLUE != 0) sts_f32_imm<2 * A_TILE>(sa, mk ? tf32_round(s2 * A) : 0.0f);     // s3 (= s2 on red K-blocks)
+    const float s2t = mk ? tf32_round(s2) : 0.0f;
+    sts_f32_imm<0>(sa, s2t);
+    if (PASS0) rp[0] = s2t;                                                          // replay copy (same swizzled layout)
+    if (BLUE != 0) {
+        const float s3t = mk ? tf32_round(s2 * A) : 0.0f;                            // s3 (= s2 on red K-blocks)
+        sts_f32_imm<2 * A_TILE>(sa, s3t);
+        if (PASS0) rp[A_TILE / 4] = s3t;
+    }
     if (PASS0) {
         const float r = rb.x;
         const float wb = wA * r;
@@ -122,11 +141,12 @@ __device__ __forceinline__ void compute_row32(const PhysConst& pc, const PixCons
 
 template <int BLUE, bool PASS0, int NR>
 __device__ __forceinline__ void kblock_consume32(const PhysConst& pc, const KBuf& kb, bool blue, uint32_t warp_sa, int nr,
-                                                 float (&E)[RPW], uint32_t& nbm) {
+                                                 float (&E)[RPW], uint32_t& nbm, float* __restrict__ rpw, int lane) {
 #pragma unroll
     for (int j = 0; j < RPW; ++j) {
         if (NR > 0 ? j < NR : j < nr)
-            compute_row32<BLUE, PASS0>(pc, kb.px, kb.r[j], blue, (warp_sa ^ ((uint32_t)j << 4)) + (uint32_t)j * 128u, E[j], nbm, j);
+            compute_row32<BLUE, PASS0>(pc, kb.px, kb.r[j], blue, (warp_sa ^ ((uint32_t)j << 4)) + (uint32_t)j * 128u, E[j], nbm, j,
+                                       rpw + ((lane ^ (j << 2)) + j * 32));
     }
 }
 
@@ -137,13 +157,14 @@ struct TcGram32Args {
     int ntiles, nkb;
     const float* PB;       // [nkb][PB32_KB_BYTES/4]
     float* gram;           // [B][G32_STRIDE]
-    long long* trace;      // debug (-DQFA_ENABLE_TRACE): CTA 0, first tile: [pass][kb][warp][4] clock64 stamps
+    float* replay;         // [gridDim.x][nkb][RP_KB_FLOATS]  s2 / s3 operand tiles of the CTA's current tile
+    long long* trace;      // debug (-DQFA_ENABLE_TRACE): CTA 0, first tile, pass 0: [kb][warp][4] clock64 stamps
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* ring = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t bar_full[NSTAGE32], bar_empty[NSTAGE32], bar_pb[NPB32], bar_gram;
+    __shared__ uint64_t bar_full[NSTAGE32], bar_empty[NSTAGE32], bar_pb[NPB32], bar_gram, bar_rp_full[RP_NST], bar_rp_empty[RP_NST];
     __shared__ uint32_t tmem_base_s;
     __shared__ float sE[TS];
     __shared__ float sNb[TS];
@@ -156,6 +177,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
     if (tid == 0) {
         for (int s = 0; s < NSTAGE32; ++s) { mbar_init(&bar_empty[s], 1); mbar_init(&bar_full[s], NWW); }
         for (int s = 0; s < NPB32; ++s) mbar_init(&bar_pb[s], 1);
+        for (int s = 0; s < RP_NST; ++s) { mbar_init(&bar_rp_full[s], 1); mbar_init(&bar_rp_empty[s], 1); }
         mbar_init(&bar_gram, 1);
         fence_mbar_init();
     }
@@ -176,19 +198,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
     }
     const int nkb = g.nkb;
 
-    uint32_t pass_iter = 0;          // counts (tile, pass) pairs of this CTA: ring / barrier parities run across passes
-    for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+    float* const rbase = g.replay + (size_t)blockIdx.x * (size_t)nkb * RP_KB_FLOATS;
+    uint32_t pass_iter = 0;          // counts (tile, pass) pairs of this CTA: image-ring / accumulator-barrier parities
+    uint32_t tile_iter = 0;          // counts tiles of this CTA: the pass-0 operand ring; 2 replay passes per tile
+    for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++tile_iter) {
         const int b0 = g.ts.first(tile);
         const int nrows = g.B - b0 < g.ts.rows(tile) ? g.B - b0 : g.ts.rows(tile);
         const int nr = warp < NWW ? (nrows - RPW * warp < 0 ? 0 : (nrows - RPW * warp > RPW ? RPW : nrows - RPW * warp)) : 0;
         for (int pass = 0; pass < NPASS; ++pass, ++pass_iter) {
-            const uint32_t git0 = pass_iter * (uint32_t)nkb;
+            const uint32_t git0 = tile_iter * (uint32_t)nkb;          // pass-0 operand ring
+            const uint32_t pit0 = pass_iter * (uint32_t)nkb;          // image ring (every pass)
             const int ncol = slice_cols(pass);
             if (warp == NWW) {
                 // ----------------------------------------------------------- CONTROL warp
                 if (elect_one()) {
-                    auto issue_pb = [&](uint32_t git, int kb) {
-                        const int slot = git % NPB32;
+                    auto issue_pb = [&](uint32_t pit, int kb) {
+                        const int slot = pit % NPB32;
                         unsigned char* dst = ring + PB32_OFF + (size_t)slot * PB32_SLOT;
                         const float* src = g.PB + (size_t)kb * (PB32_KB_BYTES / 4);
                         const uint32_t bytes = (uint32_t)ncol * 128u + (pass == 0 ? (uint32_t)H32 * 128u : 0u);
@@ -196,40 +221,82 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                         bulk_g2s(dst, src + (size_t)pass * SLICE * 32, (uint32_t)ncol * 128u, &bar_pb[slot]);
                         if (pass == 0) bulk_g2s(dst + SLICE * 128, src + (size_t)NP2_32 * 32, H32 * 128, &bar_pb[slot]);
                     };
-                    for (int kb = 0; kb < PB32_LEAD && kb < nkb; ++kb) issue_pb(git0 + kb, kb);
                     const uint32_t idA = idesc_tf32(128, ncol), idB = idesc_tf32(128, H32);
-                    for (int kb = 0; kb < nkb; ++kb) {
-                        const uint32_t git = git0 + kb;
-                        const int s = git % NSTAGE32, slot = git % NPB32;
-                        const uint32_t sb = smem_u32(ring) + (uint32_t)s * (uint32_t)STAGE32_BYTES;
-                        const uint32_t pb = smem_u32(ring) + (uint32_t)PB32_OFF + (uint32_t)slot * (uint32_t)PB32_SLOT;
-                        mbar_wait_or_trap(&bar_full[s], (git / NSTAGE32) & 1);
-                        mbar_wait_or_trap(&bar_pb[slot], (git / NPB32) & 1);
-                        fence_after_sync();
-                        const bool red = kb * KB >= Nb;        // all-red K-block: s3 = s2, wb2 = wb (two operand tiles only)
-                        const uint64_t dS2 = desc_sw128_kmajor(sb), dWb = desc_sw128_kmajor(sb + A_TILE);
-                        const uint64_t dS3 = red ? dS2 : desc_sw128_kmajor(sb + 2 * A_TILE);
-                        const uint64_t dW2 = red ? dWb : desc_sw128_kmajor(sb + 3 * A_TILE);
-                        const uint64_t dP = desc_sw128_kmajor(pb), dF = desc_sw128_kmajor(pb + SLICE * 128);
+                    if (pass == 0) {
+                        for (int kb = 0; kb < PB32_LEAD && kb < nkb; ++kb) issue_pb(pit0 + kb, kb);
+                        for (int kb = 0; kb < nkb; ++kb) {
+                            const uint32_t git = git0 + kb, pit = pit0 + kb;
+                            const int s = git % NSTAGE32, slot = pit % NPB32;
+                            const uint32_t sb = smem_u32(ring) + (uint32_t)s * (uint32_t)STAGE32_BYTES;
+                            const uint32_t pb = smem_u32(ring) + (uint32_t)PB32_OFF + (uint32_t)slot * (uint32_t)PB32_SLOT;
+                            mbar_wait_or_trap(&bar_full[s], (git / NSTAGE32) & 1);
+                            mbar_wait_or_trap(&bar_pb[slot], (pit / NPB32) & 1);
+                            fence_after_sync();
+                            const bool red = kb * KB >= Nb;        // all-red K-block: s3 = s2, wb2 = wb (two operand tiles only)
+                            const uint64_t dS2 = desc_sw128_kmajor(sb), dWb = desc_sw128_kmajor(sb + A_TILE);
+                            const uint64_t dS3 = red ? dS2 : desc_sw128_kmajor(sb + 2 * A_TILE);
+                            const uint64_t dW2 = red ? dWb : desc_sw128_kmajor(sb + 3 * A_TILE);
+                            const uint64_t dP = desc_sw128_kmajor(pb), dF = desc_sw128_kmajor(pb + SLICE * 128);
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const uint64_t ko = (uint64_t)(2 * kk);
-                            const bool acc = (kb | kk) != 0;
-                            umma_tf32(tmem + T_A, dS2 + ko, dP + ko, idA, acc);
-                            umma_tf32(tmem + T_C, dS3 + ko, dP + ko, idA, acc);
-                            if (pass == 0) {
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const uint64_t ko = (uint64_t)(2 * kk);
+                                const bool acc = (kb | kk) != 0;
+                                umma_tf32(tmem + T_A, dS2 + ko, dP + ko, idA, acc);
+                                umma_tf32(tmem + T_C, dS3 + ko, dP + ko, idA, acc);
                                 umma_tf32(tmem + T_B, dWb + ko, dF + ko, idB, acc);
                                 umma_tf32(tmem + T_D, dW2 + ko, dF + ko, idB, acc);
                             }
+                            umma_commit(&bar_empty[s]);
+                            if (kb == nkb - 1) umma_commit(&bar_gram);
+                            if (kb + PB32_LEAD < nkb) issue_pb(pit + PB32_LEAD, kb + PB32_LEAD);
                         }
-                        umma_commit(&bar_empty[s]);
-                        if (kb == nkb - 1) umma_commit(&bar_gram);
-                        if (kb + PB32_LEAD < nkb) issue_pb(git + PB32_LEAD, kb + PB32_LEAD);
+                    } else {
+                        // replay: [s2 | s3] tiles of K-block kb -> ring stage, RP_LEAD K-blocks ahead; images 2 ahead
+                        const uint32_t rit0 = (tile_iter * 2u + (uint32_t)(pass - 1)) * (uint32_t)nkb;
+                        auto issue_rp = [&](uint32_t rit, int kb) {
+                            const int s = rit % RP_NST;
+                            const uint32_t u = rit / RP_NST;
+                            if (u > 0) mbar_wait_or_trap(&bar_rp_empty[s], (u - 1) & 1);     // the MMAs that read the stage retired
+                            const bool red = kb * KB >= Nb;
+                            unsigned char* dst = ring + (size_t)s * RP_STAGE;
+                            const float* src = rbase + (size_t)kb * RP_KB_FLOATS;
+                            mbar_expect_tx(&bar_rp_full[s], red ? RP_TILE : 2 * RP_TILE);
+                            bulk_g2s(dst, src, RP_TILE, &bar_rp_full[s]);
+                            if (!red) bulk_g2s(dst + A_TILE, src + A_TILE / 4, RP_TILE, &bar_rp_full[s]);
+                        };
+                        for (int kb = 0; kb < 2 && kb < nkb; ++kb) issue_pb(pit0 + kb, kb);
+                        for (int kb = 0; kb < RP_LEAD && kb < nkb; ++kb) issue_rp(rit0 + kb, kb);
+                        for (int kb = 0; kb < nkb; ++kb) {
+                            const uint32_t rit = rit0 + kb, pit = pit0 + kb;
+                            const int s = rit % RP_NST, slot = pit % NPB32;
+                            const uint32_t sb = smem_u32(ring) + (uint32_t)s * (uint32_t)RP_STAGE;
+                            const uint32_t pb = smem_u32(ring) + (uint32_t)PB32_OFF + (uint32_t)slot * (uint32_t)PB32_SLOT;
+                            mbar_wait_or_trap(&bar_rp_full[s], (rit / RP_NST) & 1);
+                            mbar_wait_or_trap(&bar_pb[slot], (pit / NPB32) & 1);
+                            fence_after_sync();
+                            const bool red = kb * KB >= Nb;
+                            const uint64_t dS2 = desc_sw128_kmajor(sb);
+                            const uint64_t dS3 = red ? dS2 : desc_sw128_kmajor(sb + A_TILE);
+                            const uint64_t dP = desc_sw128_kmajor(pb);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const uint64_t ko = (uint64_t)(2 * kk);
+                                const bool acc = (kb | kk) != 0;
+                                umma_tf32(tmem + T_A, dS2 + ko, dP + ko, idA, acc);
+                                umma_tf32(tmem + T_C, dS3 + ko, dP + ko, idA, acc);
+                            }
+                            umma_commit(&bar_rp_empty[s]);
+                            if (kb == nkb - 1) umma_commit(&bar_gram);
+                            // stage (kb + 3) % 4 = stage of K-block kb - 1: waiting for its MMAs also frees image slot (kb + 2) % 3
+                            if (kb + RP_LEAD < nkb) issue_rp(rit + RP_LEAD, kb + RP_LEAD);
+                            else if (kb >= 1) mbar_wait_or_trap(&bar_rp_empty[(rit - 1) % RP_NST], ((rit - 1) / RP_NST) & 1);
+                            if (kb + 2 < nkb) issue_pb(pit + 2, kb + 2);
+                        }
                     }
                 }
                 __syncwarp();
-            } else {
-                // ----------------------------------------------------------- WORKER warps
+            } else if (pass == 0) {
+                // ----------------------------------------------------------- WORKER warps (pass 0 only)
                 float E[RPW];
                 uint32_t nbm = 0u;
 #pragma unroll
@@ -248,14 +315,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
 #pragma unroll
                 for (int j = 0; j < RPW; ++j) { kA.r[j].z = 0.f; kB.r[j].z = 0.f; }
                 const uint32_t ring_sa = smem_u32(ring) + (uint32_t)warp * 1024u + (uint32_t)lane * 4u;
-                auto run_kblocks = [&](auto nr_tag, auto p0_tag) {
+                float* const rpw0 = rbase + warp * 256;
+                auto run_kblocks = [&](auto nr_tag) {
                     constexpr int NR = decltype(nr_tag)::value;
-                    constexpr bool PASS0 = decltype(p0_tag)::value;
+                    constexpr bool PASS0 = true;
                     auto load_kb = [&](int kb, KBuf& k) {
                         const int p0 = kb * KB;
-                        // passes 1, 2 generate s2 / s3 only: they do not depend on delta, so it is not even loaded
-                        if (p0 + KB <= P) load_kblock<true, true, NR, PASS0>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
-                        else load_kblock<true, false, NR, PASS0>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
+                        if (p0 + KB <= P) load_kblock<true, true, NR>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
+                        else load_kblock<true, false, NR>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
                     };
                     load_kb(0, kA);
                     if (nkb > 1) load_kb(1, kB);
@@ -266,15 +333,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                         const int p0 = kb * KB;
                         const bool blue = p0 + lane < Nb;
                         long long* tr = (kTrace && g.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && lane == 0)
-                                            ? g.trace + (((size_t)pass * nkb + kb) * NPW + warp) * 4 : nullptr;
+                                            ? g.trace + ((size_t)kb * NPW + warp) * 4 : nullptr;
                         if (tr) tr[0] = clock64();
                         if (u > 0) mbar_wait_or_trap(&bar_empty[s], (u - 1) & 1);
                         if (tr) tr[1] = clock64();
                         const uint32_t stage_sa = ring_sa + (uint32_t)s * (uint32_t)STAGE32_BYTES;
+                        float* const rpw = rpw0 + (size_t)kb * RP_KB_FLOATS;
                         const int bm = (p0 + KB <= Nb) ? 1 : (p0 >= Nb ? 0 : 2);
-                        if (bm == 1) kblock_consume32<1, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
-                        else if (bm == 0) kblock_consume32<0, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
-                        else kblock_consume32<2, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
+                        if (bm == 1) kblock_consume32<1, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm, rpw, lane);
+                        else if (bm == 0) kblock_consume32<0, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm, rpw, lane);
+                        else kblock_consume32<2, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm, rpw, lane);
                         if (tr) tr[2] = clock64();
                         fence_proxy_async();            // MEMBAR.ALL.CTA: before the prefetch below, never after it
                         __syncwarp();
@@ -287,19 +355,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                         if (kb + 1 < nkb) do_kblock(kb + 1, kB);
                     }
                 };
-                if (pass == 0) {
-                    if (nr == RPW) run_kblocks(std::integral_constant<int, RPW>{}, std::true_type{});
-                    else run_kblocks(std::integral_constant<int, 0>{}, std::true_type{});
+                if (nr == RPW) run_kblocks(std::integral_constant<int, RPW>{});
+                else run_kblocks(std::integral_constant<int, 0>{});
 #pragma unroll
-                    for (int j = 0; j < RPW; ++j) {
-                        const float e = warp_sum(E[j]);
-                        const bool any = __any_sync(0xffffffffu, (nbm >> j) & 1u);
-                        if (lane == 0) { sE[RPW * warp + j] = e; sNb[RPW * warp + j] = any ? 1.0f : 0.0f; }
-                    }
-                } else {
-                    if (nr == RPW) run_kblocks(std::integral_constant<int, RPW>{}, std::false_type{});
-                    else run_kblocks(std::integral_constant<int, 0>{}, std::false_type{});
+                for (int j = 0; j < RPW; ++j) {
+                    const float e = warp_sum(E[j]);
+                    const bool any = __any_sync(0xffffffffu, (nbm >> j) & 1u);
+                    if (lane == 0) { sE[RPW * warp + j] = e; sNb[RPW * warp + j] = any ? 1.0f : 0.0f; }
                 }
+                // the replay tiles were written through the generic proxy and are read back by bulk copies (async proxy)
+                asm volatile("fence.proxy.async.global;" ::: "memory");
             }
             named_bar_sync(1, NTHREADS);            // sE / sNb visible; every worker is done with the ring
             // ----------------------------------------------------------- drain the accumulators (warps 0..3: lane = spectrum row)
@@ -557,6 +622,7 @@ struct TcGrad32Args {
     int B;
     int nsplit;            // CTAs per pixel tile; grid = (npix_tiles, nsplit)
     const float* img;      // [B (+2 pad)][G32_IMG/4]  images written by k_solve32
+    long long* trace;      // debug (-DQFA_ENABLE_TRACE): CTA (0,0), first 256 steps: [step][8] clock64 stamps
     float* part;           // [nsplit][part_len]
     float* spart;          // [nsplit][npix_tiles][3]
 };
@@ -623,9 +689,9 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
     if (warp == G32_W) {
         // =============================================================== CONTROL warp
         if (nst > 0 && elect_one()) {
-            const uint32_t idN = idesc_tf32(128, G32_ROWS);
+            const uint32_t idN = idesc_tf32(128, G32_SPS * G32_ROWS);     // the 3 images of a stage are ONE 240-row B operand
             auto issue_b = [&](int n) {           // images of step n -> ring stage n % 4
-                const int s = n % G32_NST;
+                const int s = n % G32_NST;              // (single thread, off the critical chain)
                 const size_t b0 = (size_t)(st0 + n) * G32_SPS;
                 mbar_expect_tx(&bar_b[s], G32_SPS * G32_LIVE);
 #pragma unroll
@@ -637,18 +703,22 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
             for (int n = 0; n < nst; ++n) {
                 const int buf = n & 1, s = n % G32_NST;
                 // workers have drained TMEM buffer `buf` (step n-2): its MMAs retired long ago, so ring stage (n+2) % 4 = (n-2) % 4 is free
+                long long* tr = (kTrace && g.trace && blockIdx.x == 0 && blockIdx.y == 0 && n < 256) ? g.trace + n * 8 : nullptr;
+                if (tr) tr[0] = clock64();
                 if (n >= 2) mbar_wait_or_trap(&bar_tm_empty[buf], ((n >> 1) - 1) & 1);
-                if (n + 2 < nst) issue_b(n + 2);
+                if (tr) tr[1] = clock64();
                 mbar_wait_or_trap(&bar_b[s], (n / G32_NST) & 1);
                 fence_after_sync();
-#pragma unroll
-                for (int sp = 0; sp < G32_SPS; ++sp) {
-                    const uint64_t dB = desc_sw128_kmajor(sm_sa + G32_B_OFF + s * G32_STAGE + sp * G32_IMG);
-                    const uint32_t dcol = tmem + buf * G32_TBUF + sp * G32_ROWS;
+                if (tr) tr[2] = clock64();
+                {
+                    const uint64_t dB = desc_sw128_kmajor(sm_sa + G32_B_OFF + s * G32_STAGE);
+                    const uint32_t dcol = tmem + buf * G32_TBUF;
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) umma_tf32(dcol, dA + (uint64_t)(2 * kk), dB + (uint64_t)(2 * kk), idN, kk > 0);
                 }
                 umma_commit(&bar_tm_full[buf]);
+                if (n + 2 < nst) issue_b(n + 2);          // after the MMAs: off the empty -> full critical chain
+                if (tr) tr[3] = clock64();
             }
         }
         __syncwarp();
@@ -663,39 +733,59 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
         const float tau0 = __ldg(f.scal + 0), c0s = __ldg(f.scal + 1), beta = __ldg(f.scal + 2);
         const float one_m_c0 = 1.0f - c0s, nt0l2e = -tau0 * kLog2e, l2zn = f.llogzn * kLog2e;
         struct Cell { float x, e, z; unsigned m; };
-        auto load_cell = [&](int n, Cell& c) {
-            const int b = (st0 + n) * G32_SPS + grp;
-            if (pix_ok && b < g.B) {
-                const size_t o = (size_t)b * P + i;
-                c.m = ldg_stream_u8(f.mask + o);
-                c.x = ldg_stream(f.x + o);
-                c.e = ldg_stream(f.err + o);
-                c.z = any_blue ? ldg_stream(f.zabs + (size_t)b * Nb + iz) : 0.f;
+        // cells are requested strictly in step order: running pointers (one 64-bit add each per step, no multiplies)
+        const size_t o0 = (size_t)(st0 * G32_SPS + grp) * P + ic;
+        const float* cx = f.x + o0;
+        const float* ce = f.err + o0;
+        const uint8_t* cm = f.mask + o0;
+        const float* cz = f.zabs + (size_t)(st0 * G32_SPS + grp) * Nb + iz;
+        const size_t cstride = (size_t)G32_SPS * P, zstride = (size_t)G32_SPS * Nb;
+        int cleft = pix_ok ? (g.B - grp + G32_SPS - 1) / G32_SPS - st0 : 0;       // steps whose spectrum exists
+        auto load_cell = [&](int, Cell& c) {
+            if (cleft > 0) {
+                c.m = ldg_stream_u8(cm);
+                c.x = ldg_stream(cx);
+                c.e = ldg_stream(ce);
+                c.z = any_blue ? ldg_stream(cz) : 0.f;
             } else { c.m = 0u; c.x = 0.f; c.e = 1.f; c.z = 0.f; }
+            --cleft; cx += cstride; ce += cstride; cm += cstride; cz += zstride;
         };
-        Cell cA, cB;
-        if (nst > 0) load_cell(0, cA);
-        if (nst > 1) load_cell(1, cB);
+        // the cell of step n is requested G32_CELL_LEAD steps (>= 2 us) ahead: one step is less than the loaded HBM latency
+        Cell cc[G32_CELL_LEAD];
+#pragma unroll
+        for (int q = 0; q < G32_CELL_LEAD; ++q)
+            if (q < nst) load_cell(q, cc[q]);
+        int wstage = 0;                                    // ring stage of the next step (n % G32_NST without the division)
         auto do_step = [&](int n, Cell& cb) {
-            const int buf = n & 1, s = n % G32_NST;
+            const int buf = n & 1, s = wstage;
+            wstage = wstage + 1 == G32_NST ? 0 : wstage + 1;
             const int b = (st0 + n) * G32_SPS + grp;
             const bool valid = b < g.B;                       // warp-uniform
+            long long* tr = (kTrace && g.trace && blockIdx.x == 0 && blockIdx.y == 0 && n < 256 && warp == 5 && lane == 0)
+                                ? g.trace + n * 8 : nullptr;
+            if (tr) tr[4] = clock64();
             mbar_wait_or_trap(&bar_tm_full[buf], (n >> 1) & 1);
             fence_after_sync();
+            if (tr) tr[5] = clock64();
             const uint32_t tcol = ta + buf * G32_TBUF + grp * G32_ROWS;
-            float q = 0.f, fa = 0.f;
-            {
-                float z[16];
-                tmem_ld16(tcol + 32, z); tmem_wait_ld();
+            // The TMEM buffer is handed back as soon as its 65 columns are in registers, BEFORE the math: the control warp then
+            // runs a full step ahead and the workers never wait for an accumulator.  (The ring stage is still read below -- c,
+            // image row 65 -- which is why the ring has 5 stages: the copy for step n+2 goes to the stage of step n-3.)
+            float z[2][16], y[2][16], w8[8];
+            tmem_ld16(tcol + 32, z[0]); tmem_ld16(tcol + 48, z[1]); tmem_ld8(tcol + 64, w8);
+            tmem_wait_ld();
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-                for (int t = 0; t < 16; ++t) q = fmaf(z[t], z[t], q);
-                tmem_ld16(tcol + 48, z); tmem_wait_ld();
-#pragma unroll
-                for (int t = 0; t < 16; ++t) q = fmaf(z[t], z[t], q);
-                float w8[8];
-                tmem_ld8(tcol + 64, w8); tmem_wait_ld();
-                fa = w8[0];
+            for (int t = 0; t < 16; t += 2) {
+                q0 = fmaf(z[0][t], z[0][t], q0); q1 = fmaf(z[0][t + 1], z[0][t + 1], q1);
+                q2 = fmaf(z[1][t], z[1][t], q2); q3 = fmaf(z[1][t + 1], z[1][t + 1], q3);
             }
+            tmem_ld16(tcol, y[0]); tmem_ld16(tcol + 16, y[1]);
+            tmem_wait_ld();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tm_empty[buf]);
+            const float q = (q0 + q1) + (q2 + q3), fa = w8[0];
             const bool mk = cb.m != 0u && valid;
             float A = 1.0f, zdep = 0.0f, powb = 0.0f, L2 = 0.0f;
             if (any_blue) {
@@ -731,30 +821,26 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
                 }
                 // gradF: - s2 (f^T K)_k - (A u) c_k ; c_b = image row 65 (shared memory, broadcast reads)
                 const uint32_t crow = sm_sa + G32_B_OFF + (uint32_t)s * G32_STAGE + (uint32_t)grp * G32_IMG;
+                const float ns2 = -s2, nAu = -Au;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float y[16];
-                    tmem_ld16(tcol + 16 * h, y); tmem_wait_ld();
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        float cx, cy, cz, cw;
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cx), "=f"(cy), "=f"(cz), "=f"(cw)
-                                     : "r"(crow + sw128_offset(65, 16 * h + 4 * c4)));
-                        gF[16 * h + 4 * c4 + 0] -= fmaf(s2, y[4 * c4 + 0], Au * cx);
-                        gF[16 * h + 4 * c4 + 1] -= fmaf(s2, y[4 * c4 + 1], Au * cy);
-                        gF[16 * h + 4 * c4 + 2] -= fmaf(s2, y[4 * c4 + 2], Au * cz);
-                        gF[16 * h + 4 * c4 + 3] -= fmaf(s2, y[4 * c4 + 3], Au * cw);
-                    }
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    float cx, cy, cz, cw;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cx), "=f"(cy), "=f"(cz), "=f"(cw)
+                                 : "r"(crow + sw128_offset(65, 4 * c4)));
+                    const int k = 4 * c4;
+                    gF[k] = fmaf(ns2, y[k >> 4][k & 15], fmaf(nAu, cx, gF[k]));
+                    gF[k + 1] = fmaf(ns2, y[k >> 4][(k & 15) + 1], fmaf(nAu, cy, gF[k + 1]));
+                    gF[k + 2] = fmaf(ns2, y[k >> 4][(k & 15) + 2], fmaf(nAu, cz, gF[k + 2]));
+                    gF[k + 3] = fmaf(ns2, y[k >> 4][(k & 15) + 3], fmaf(nAu, cw, gF[k + 3]));
                 }
             }
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tm_empty[buf]);
-            if (n + 2 < nst) load_cell(n + 2, cb);
+            if (tr) tr[6] = clock64();
+            if (n + G32_CELL_LEAD < nst) load_cell(n + G32_CELL_LEAD, cb);
         };
-        for (int n = 0; n < nst; n += 2) {
-            do_step(n, cA);
-            if (n + 1 < nst) do_step(n + 1, cB);
+        for (int n = 0; n < nst; n += G32_CELL_LEAD) {
+#pragma unroll
+            for (int q = 0; q < G32_CELL_LEAD; ++q)
+                if (n + q < nst) do_step(n + q, cc[q]);
         }
     }
 
