@@ -518,7 +518,22 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceArgs<T> r) {
         // last block additionally folds the per-spectrum scalars (block-strided, fixed tree)
         __shared__ T red[4 * 32];
         T v[2] = {T(0), T(0)};
-        for (int b = threadIdx.x; b < r.B; b += blockDim.x) {
+        // contiguous per-spectrum arrays (65 536 values for one block): four elements per thread and trip, trips unrolled, so
+        // that 16 loads per array are in flight instead of one (the fold was 0.13 ms of the Nh 32 step)
+        int b_lo = 0;
+        if (r.stride == 1) {
+            const int B4 = r.B & ~3;
+#pragma unroll 4
+            for (int b = threadIdx.x * 4; b < B4; b += blockDim.x * 4) {
+                T n4[4]; float h4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { n4[q] = r.nll[b + q]; h4[q] = r.hasblue[b + q]; }
+                v[0] += (n4[0] + n4[1]) + (n4[2] + n4[3]);
+                v[1] += (T)((h4[0] + h4[1]) + (h4[2] + h4[3]));
+            }
+            b_lo = B4;
+        }
+        for (int b = b_lo + threadIdx.x; b < r.B; b += blockDim.x) {
             v[0] += r.nll[(size_t)b * r.stride];
             v[1] += (T)r.hasblue[(size_t)b * r.stride];
         }

@@ -101,7 +101,7 @@ __global__ void k_tc_build_images32(const float* __restrict__ F, int P, int Nh, 
 // per-cell physics + operand generation; PASS0 also produces the wb / wb2 operands and the scalar sums
 template <int BLUE, bool PASS0>
 __device__ __forceinline__ void compute_row32(const PhysConst& pc, const PixConst& px, const RowBuf& rb, bool blue, uint32_t sa,
-                                              float& E, uint32_t& nbm, int j, float* __restrict__ rp) {
+                                              float& E, uint32_t& nbm, int j) {
     const bool mk = rb.m != 0u;
     float A = 1.0f, oz = 0.0f;
     if (BLUE != 0) {
@@ -118,14 +118,8 @@ __device__ __forceinline__ void compute_row32(const PhysConst& pc, const PixCons
     const float w = rcpf(D);
     const float wA = w * A;
     const float s2 = wA * A;
-    const float s2t = mk ? tf32_round(s2) : 0.0f;
-    sts_f32_imm<0>(sa, s2t);
-    if (PASS0) rp[0] = s2t;                                                          // replay copy (same swizzled layout)
-    if (BLUE != 0) {
-        const float s3t = mk ? tf32_round(s2 * A) : 0.0f;                            // s3 (= s2 on red K-blocks)
-        sts_f32_imm<2 * A_TILE>(sa, s3t);
-        if (PASS0) rp[A_TILE / 4] = s3t;
-    }
+    sts_f32_imm<0>(sa, mk ? tf32_round(s2) : 0.0f);
+    if (BLUE != 0) sts_f32_imm<2 * A_TILE>(sa, mk ? tf32_round(s2 * A) : 0.0f);     // s3 (= s2 on red K-blocks)
     if (PASS0) {
         const float r = rb.x;
         const float wb = wA * r;
@@ -141,12 +135,11 @@ __device__ __forceinline__ void compute_row32(const PhysConst& pc, const PixCons
 
 template <int BLUE, bool PASS0, int NR>
 __device__ __forceinline__ void kblock_consume32(const PhysConst& pc, const KBuf& kb, bool blue, uint32_t warp_sa, int nr,
-                                                 float (&E)[RPW], uint32_t& nbm, float* __restrict__ rpw, int lane) {
+                                                 float (&E)[RPW], uint32_t& nbm) {
 #pragma unroll
     for (int j = 0; j < RPW; ++j) {
         if (NR > 0 ? j < NR : j < nr)
-            compute_row32<BLUE, PASS0>(pc, kb.px, kb.r[j], blue, (warp_sa ^ ((uint32_t)j << 4)) + (uint32_t)j * 128u, E[j], nbm, j,
-                                       rpw + ((lane ^ (j << 2)) + j * 32));
+            compute_row32<BLUE, PASS0>(pc, kb.px, kb.r[j], blue, (warp_sa ^ ((uint32_t)j << 4)) + (uint32_t)j * 128u, E[j], nbm, j);
     }
 }
 
@@ -175,7 +168,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
     const int P = f.P, Nb = f.Nb;
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE32; ++s) { mbar_init(&bar_empty[s], 1); mbar_init(&bar_full[s], NWW); }
+        for (int s = 0; s < NSTAGE32; ++s) { mbar_init(&bar_empty[s], 2); mbar_init(&bar_full[s], NWW); }   // empty: MMAs retired + replay copy read
         for (int s = 0; s < NPB32; ++s) mbar_init(&bar_pb[s], 1);
         for (int s = 0; s < RP_NST; ++s) { mbar_init(&bar_rp_full[s], 1); mbar_init(&bar_rp_empty[s], 1); }
         mbar_init(&bar_gram, 1);
@@ -230,6 +223,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                             const uint32_t sb = smem_u32(ring) + (uint32_t)s * (uint32_t)STAGE32_BYTES;
                             const uint32_t pb = smem_u32(ring) + (uint32_t)PB32_OFF + (uint32_t)slot * (uint32_t)PB32_SLOT;
                             mbar_wait_or_trap(&bar_full[s], (git / NSTAGE32) & 1);
+                            fence_proxy_async_issuer();
                             mbar_wait_or_trap(&bar_pb[slot], (pit / NPB32) & 1);
                             fence_after_sync();
                             const bool red = kb * KB >= Nb;        // all-red K-block: s3 = s2, wb2 = wb (two operand tiles only)
@@ -249,7 +243,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                             umma_commit(&bar_empty[s]);
                             if (kb == nkb - 1) umma_commit(&bar_gram);
                             if (kb + PB32_LEAD < nkb) issue_pb(pit + PB32_LEAD, kb + PB32_LEAD);
+                            // replay copy of the s2 / s3 tiles, shared -> global through the async proxy (the workers' stores
+                            // are already fenced for it); the stage goes back to the workers when the MMAs have retired AND
+                            // this copy has read it
+                            float* rp = rbase + (size_t)kb * RP_KB_FLOATS;
+                            bulk_s2g(rp, sb, RP_TILE);
+                            if (!red) bulk_s2g(rp + A_TILE / 4, sb + 2 * A_TILE, RP_TILE);
+                            bulk_commit_group();
+                            bulk_wait_group_read0();
+                            mbar_arrive(&bar_empty[s]);
                         }
+                        bulk_wait_group0();              // replay tiles are in global memory before pass 1 reads them back
                     } else {
                         // replay: [s2 | s3] tiles of K-block kb -> ring stage, RP_LEAD K-blocks ahead; images 2 ahead
                         const uint32_t rit0 = (tile_iter * 2u + (uint32_t)(pass - 1)) * (uint32_t)nkb;
@@ -271,9 +275,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                             const int s = rit % RP_NST, slot = pit % NPB32;
                             const uint32_t sb = smem_u32(ring) + (uint32_t)s * (uint32_t)RP_STAGE;
                             const uint32_t pb = smem_u32(ring) + (uint32_t)PB32_OFF + (uint32_t)slot * (uint32_t)PB32_SLOT;
+                            long long* tr = (kTrace && g.trace && blockIdx.x == 0 && tile == (int)blockIdx.x)
+                                                ? g.trace + (size_t)nkb * NPW * 4 + ((size_t)(pass - 1) * nkb + kb) * 8 : nullptr;
+                            if (tr) tr[0] = clock64();
                             mbar_wait_or_trap(&bar_rp_full[s], (rit / RP_NST) & 1);
+                            if (tr) tr[1] = clock64();
                             mbar_wait_or_trap(&bar_pb[slot], (pit / NPB32) & 1);
                             fence_after_sync();
+                            if (tr) tr[2] = clock64();
                             const bool red = kb * KB >= Nb;
                             const uint64_t dS2 = desc_sw128_kmajor(sb);
                             const uint64_t dS3 = red ? dS2 : desc_sw128_kmajor(sb + A_TILE);
@@ -287,10 +296,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                             }
                             umma_commit(&bar_rp_empty[s]);
                             if (kb == nkb - 1) umma_commit(&bar_gram);
+                            if (tr) tr[3] = clock64();
                             // stage (kb + 3) % 4 = stage of K-block kb - 1: waiting for its MMAs also frees image slot (kb + 2) % 3
                             if (kb + RP_LEAD < nkb) issue_rp(rit + RP_LEAD, kb + RP_LEAD);
                             else if (kb >= 1) mbar_wait_or_trap(&bar_rp_empty[(rit - 1) % RP_NST], ((rit - 1) / RP_NST) & 1);
                             if (kb + 2 < nkb) issue_pb(pit + 2, kb + 2);
+                            if (tr) tr[4] = clock64();
                         }
                     }
                 }
@@ -315,7 +326,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
 #pragma unroll
                 for (int j = 0; j < RPW; ++j) { kA.r[j].z = 0.f; kB.r[j].z = 0.f; }
                 const uint32_t ring_sa = smem_u32(ring) + (uint32_t)warp * 1024u + (uint32_t)lane * 4u;
-                float* const rpw0 = rbase + warp * 256;
                 auto run_kblocks = [&](auto nr_tag) {
                     constexpr int NR = decltype(nr_tag)::value;
                     constexpr bool PASS0 = true;
@@ -338,13 +348,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                         if (u > 0) mbar_wait_or_trap(&bar_empty[s], (u - 1) & 1);
                         if (tr) tr[1] = clock64();
                         const uint32_t stage_sa = ring_sa + (uint32_t)s * (uint32_t)STAGE32_BYTES;
-                        float* const rpw = rpw0 + (size_t)kb * RP_KB_FLOATS;
                         const int bm = (p0 + KB <= Nb) ? 1 : (p0 >= Nb ? 0 : 2);
-                        if (bm == 1) kblock_consume32<1, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm, rpw, lane);
-                        else if (bm == 0) kblock_consume32<0, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm, rpw, lane);
-                        else kblock_consume32<2, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm, rpw, lane);
+                        if (bm == 1) kblock_consume32<1, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
+                        else if (bm == 0) kblock_consume32<0, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
+                        else kblock_consume32<2, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
                         if (tr) tr[2] = clock64();
-                        fence_proxy_async();            // MEMBAR.ALL.CTA: before the prefetch below, never after it
+                        fence_proxy_async_writer();     // MEMBAR.ALL.CTA: before the prefetch below, never after it
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bar_full[s]);
                         if (kb + 2 < nkb) load_kb(kb + 2, k);
@@ -363,8 +372,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                     const bool any = __any_sync(0xffffffffu, (nbm >> j) & 1u);
                     if (lane == 0) { sE[RPW * warp + j] = e; sNb[RPW * warp + j] = any ? 1.0f : 0.0f; }
                 }
-                // the replay tiles were written through the generic proxy and are read back by bulk copies (async proxy)
-                asm volatile("fence.proxy.async.global;" ::: "memory");
             }
             named_bar_sync(1, NTHREADS);            // sE / sNb visible; every worker is done with the ring
             // ----------------------------------------------------------- drain the accumulators (warps 0..3: lane = spectrum row)

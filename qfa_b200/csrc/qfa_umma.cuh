@@ -44,6 +44,17 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
 // ------------------------------------------------------------------ async-proxy plumbing
 // generic-proxy smem writes (st.shared) -> visible to the async proxy (tcgen05.mma / bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Where the generic-proxy writes of an operand tile are fenced for the async proxy (tcgen05.mma).  Default: by every WRITER
+// before its mbarrier arrive (the documented pattern).  -DQFA_CONSUMER_FENCE: by the ISSUING thread after its mbarrier wait
+// (the writers' stores are ordered before the fence by the arrive/wait pair) -- the writers then execute no MEMBAR, which
+// otherwise waits for every global load they have in flight.
+#ifdef QFA_CONSUMER_FENCE
+__device__ __forceinline__ void fence_proxy_async_writer() {}
+__device__ __forceinline__ void fence_proxy_async_issuer() { fence_proxy_async(); }
+#else
+__device__ __forceinline__ void fence_proxy_async_writer() { fence_proxy_async(); }
+__device__ __forceinline__ void fence_proxy_async_issuer() {}
+#endif
 
 // 1-D bulk copy global -> shared (TMA, SASS UBLKCP); 16-byte aligned src/dst/size
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
@@ -52,6 +63,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+
+// 1-D bulk copy shared -> global (bulk-group completion); 16-byte aligned src/dst/size
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all bulk groups of this thread are complete (writes performed)
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------ TMEM
 template <int NCOLS>
