@@ -142,6 +142,27 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """File descriptor 1 is pointed at stderr for the whole run, so that nothing a library writes to stdout (NCCL banner,
+    warnings) can precede the JSON line; emit() writes that line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def dist_setup(n):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -149,7 +170,8 @@ def dist_setup(n):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION: keep stdout to the one JSON line
+        # NCCL prints its version banner on STDOUT (NCCL_DEBUG=VERSION, also from an nccl.conf): stdout carries the one JSON
+        # line only -- see emit()
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -223,7 +245,7 @@ def run_reference(args):
             "config": {"workload": args.workload, "kind": kind, "grid": grid_name, "Nh": Nh},
             "cpu_baseline": {"value": v, "unit": "spectra/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -338,10 +360,11 @@ def measure_workload(name, args, rank, world, peaks, want_e2e, want_cpu, nspec_o
 
 def main():
     args = parse()
+    capture_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: the QFA kernels have no CPU fallback"}))
+        emit({"error": "no CUDA device: the QFA kernels have no CPU fallback"})
         sys.exit(1)
     rank, world, local = dist_setup(args.gpus)
     torch.cuda.set_device(local)
@@ -385,7 +408,7 @@ def main():
             line["cpu_baseline"] = main_res["cpu_baseline"]
         if also:
             line["also"] = also
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
