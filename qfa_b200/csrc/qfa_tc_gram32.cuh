@@ -143,6 +143,90 @@ __device__ __forceinline__ void kblock_consume32(const PhysConst& pc, const KBuf
     }
 }
 
+// Pass 0 of one tile for one worker warp: generate the operand tiles K-block by K-block.  A separate NON-INLINED function:
+// inlined into the kernel, the tile / pass loop state around it pushed the two prefetch buffers (64 registers) into local
+// memory, and a load whose result is spilled must be waited for on the spot -- every K-block then paid the full memory
+// latency (period 6 200 cycles, 3 600 of them in the load phase).
+struct G32Worker {
+    const float* x; const float* err; const float* zabs; const uint8_t* mask;   // row 0 of the tile
+    const float* Psi; const float* omega; const uint8_t* zero;
+    int P, Nb, nkb, nr, warp, lane;
+    uint32_t git0, ring_sa;
+    uint64_t* bar_full; uint64_t* bar_empty;
+    float* sE; float* sNb;
+    long long* trace;
+};
+
+__device__ __noinline__ void gram32_pass0_worker(const G32Worker w, const PhysConst pc) {
+    const int P = w.P, Nb = w.Nb, nkb = w.nkb, nr = w.nr, warp = w.warp, lane = w.lane;
+    Field<float> f;
+    f.P = P; f.Nb = Nb; f.Psi = w.Psi; f.omega = w.omega; f.mu = nullptr;
+    float E[RPW];
+    uint32_t nbm = 0u;
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) E[j] = 0.f;
+    TileView tv;
+    tv.zero = w.zero;
+    RowCursor rc;
+    rc.x = reinterpret_cast<const unsigned char*>(w.x + (size_t)(RPW * warp) * P + lane);
+    rc.e = reinterpret_cast<const unsigned char*>(w.err + (size_t)(RPW * warp) * P + lane);
+    rc.m = w.mask + (size_t)(RPW * warp) * P + lane;
+    rc.z = reinterpret_cast<const unsigned char*>(w.zabs + (size_t)(RPW * warp) * Nb + lane);
+    KBuf kA, kB;
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) { kA.r[j].z = 0.f; kB.r[j].z = 0.f; }
+    const uint32_t ring_sa = w.ring_sa, git0 = w.git0;
+    uint64_t* const bar_full = w.bar_full;
+    uint64_t* const bar_empty = w.bar_empty;
+    auto run_kblocks = [&](auto nr_tag) {
+        constexpr int NR = decltype(nr_tag)::value;
+        constexpr bool PASS0 = true;
+        auto load_kb = [&](int kb, KBuf& k) {
+            const int p0 = kb * KB;
+            if (p0 + KB <= P) load_kblock<true, true, NR>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
+            else load_kblock<true, false, NR>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
+        };
+        load_kb(0, kA);
+        if (nkb > 1) load_kb(1, kB);
+        auto do_kblock = [&](int kb, KBuf& k) {
+            const uint32_t git = git0 + kb;
+            const int s = git % NSTAGE32;
+            const uint32_t u = git / NSTAGE32;
+            const int p0 = kb * KB;
+            const bool blue = p0 + lane < Nb;
+            long long* tr = (kTrace && w.trace) ? w.trace + (size_t)kb * NPW * 4 : nullptr;
+            if (tr) tr[0] = clock64();
+            if (u > 0) mbar_wait_or_trap(&bar_empty[s], (u - 1) & 1);
+            if (tr) tr[1] = clock64();
+            const uint32_t stage_sa = ring_sa + (uint32_t)s * (uint32_t)STAGE32_BYTES;
+            const int bm = (p0 + KB <= Nb) ? 1 : (p0 >= Nb ? 0 : 2);
+            if (bm == 1) kblock_consume32<1, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
+            else if (bm == 0) kblock_consume32<0, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
+            else kblock_consume32<2, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
+            if (tr) tr[2] = clock64();
+            fence_proxy_async_writer();     // MEMBAR.ALL.CTA: before the prefetch below, never after it
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_full[s]);
+            if (kb + 2 < nkb) load_kb(kb + 2, k);
+            if (tr) tr[3] = clock64();
+        };
+        // (tried: a loop of their own for the all-red K-blocks, where the 16 `z` registers are dead -- still 10 spilled
+        //  prefetch registers per K-block there, and any spilled load result makes the load phase wait: no gain)
+        for (int kb = 0; kb < nkb; kb += 2) {
+            do_kblock(kb, kA);
+            if (kb + 1 < nkb) do_kblock(kb + 1, kB);
+        }
+    };
+    if (nr == RPW) run_kblocks(std::integral_constant<int, RPW>{});
+    else run_kblocks(std::integral_constant<int, 0>{});
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+        const float e = warp_sum(E[j]);
+        const bool any = __any_sync(0xffffffffu, (nbm >> j) & 1u);
+        if (lane == 0) { w.sE[j] = e; w.sNb[j] = any ? 1.0f : 0.0f; }
+    }
+}
+
 struct TcGram32Args {
     Field<float> f;
     int B;
@@ -191,7 +275,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
     }
     const int nkb = g.nkb;
 
-    float* const rbase = g.replay + (size_t)blockIdx.x * (size_t)nkb * RP_KB_FLOATS;
     uint32_t pass_iter = 0;          // counts (tile, pass) pairs of this CTA: image-ring / accumulator-barrier parities
     uint32_t tile_iter = 0;          // counts tiles of this CTA: the pass-0 operand ring; 2 replay passes per tile
     for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++tile_iter) {
@@ -205,6 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
             if (warp == NWW) {
                 // ----------------------------------------------------------- CONTROL warp
                 if (elect_one()) {
+                    float* const rbase = g.replay + (size_t)blockIdx.x * (size_t)nkb * RP_KB_FLOATS;
                     auto issue_pb = [&](uint32_t pit, int kb) {
                         const int slot = pit % NPB32;
                         unsigned char* dst = ring + PB32_OFF + (size_t)slot * PB32_SLOT;
@@ -308,70 +392,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                 __syncwarp();
             } else if (pass == 0) {
                 // ----------------------------------------------------------- WORKER warps (pass 0 only)
-                float E[RPW];
-                uint32_t nbm = 0u;
-#pragma unroll
-                for (int j = 0; j < RPW; ++j) E[j] = 0.f;
-                TileView tv;
-                tv.x = f.x + (size_t)b0 * P; tv.err = f.err + (size_t)b0 * P; tv.mask = f.mask + (size_t)b0 * P;
-                tv.zabs = f.zabs + (size_t)b0 * Nb;
-                tv.nrows = nrows;
-                tv.zero = reinterpret_cast<const uint8_t*>(g.PB + (size_t)nkb * (PB32_KB_BYTES / 4));   // 16 zero bytes after the image
-                RowCursor rc;
-                rc.x = reinterpret_cast<const unsigned char*>(tv.x + (size_t)(RPW * warp) * P + lane);
-                rc.e = reinterpret_cast<const unsigned char*>(tv.err + (size_t)(RPW * warp) * P + lane);
-                rc.m = tv.mask + (size_t)(RPW * warp) * P + lane;
-                rc.z = reinterpret_cast<const unsigned char*>(tv.zabs + (size_t)(RPW * warp) * Nb + lane);
-                KBuf kA, kB;
-#pragma unroll
-                for (int j = 0; j < RPW; ++j) { kA.r[j].z = 0.f; kB.r[j].z = 0.f; }
-                const uint32_t ring_sa = smem_u32(ring) + (uint32_t)warp * 1024u + (uint32_t)lane * 4u;
-                auto run_kblocks = [&](auto nr_tag) {
-                    constexpr int NR = decltype(nr_tag)::value;
-                    constexpr bool PASS0 = true;
-                    auto load_kb = [&](int kb, KBuf& k) {
-                        const int p0 = kb * KB;
-                        if (p0 + KB <= P) load_kblock<true, true, NR>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
-                        else load_kblock<true, false, NR>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
-                    };
-                    load_kb(0, kA);
-                    if (nkb > 1) load_kb(1, kB);
-                    auto do_kblock = [&](int kb, KBuf& k) {
-                        const uint32_t git = git0 + kb;
-                        const int s = git % NSTAGE32;
-                        const uint32_t u = git / NSTAGE32;
-                        const int p0 = kb * KB;
-                        const bool blue = p0 + lane < Nb;
-                        long long* tr = (kTrace && g.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && lane == 0)
-                                            ? g.trace + ((size_t)kb * NPW + warp) * 4 : nullptr;
-                        if (tr) tr[0] = clock64();
-                        if (u > 0) mbar_wait_or_trap(&bar_empty[s], (u - 1) & 1);
-                        if (tr) tr[1] = clock64();
-                        const uint32_t stage_sa = ring_sa + (uint32_t)s * (uint32_t)STAGE32_BYTES;
-                        const int bm = (p0 + KB <= Nb) ? 1 : (p0 >= Nb ? 0 : 2);
-                        if (bm == 1) kblock_consume32<1, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
-                        else if (bm == 0) kblock_consume32<0, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
-                        else kblock_consume32<2, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
-                        if (tr) tr[2] = clock64();
-                        fence_proxy_async_writer();     // MEMBAR.ALL.CTA: before the prefetch below, never after it
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar_full[s]);
-                        if (kb + 2 < nkb) load_kb(kb + 2, k);
-                        if (tr) tr[3] = clock64();
-                    };
-                    for (int kb = 0; kb < nkb; kb += 2) {
-                        do_kblock(kb, kA);
-                        if (kb + 1 < nkb) do_kblock(kb + 1, kB);
-                    }
-                };
-                if (nr == RPW) run_kblocks(std::integral_constant<int, RPW>{});
-                else run_kblocks(std::integral_constant<int, 0>{});
-#pragma unroll
-                for (int j = 0; j < RPW; ++j) {
-                    const float e = warp_sum(E[j]);
-                    const bool any = __any_sync(0xffffffffu, (nbm >> j) & 1u);
-                    if (lane == 0) { sE[RPW * warp + j] = e; sNb[RPW * warp + j] = any ? 1.0f : 0.0f; }
-                }
+                G32Worker wa;
+                wa.x = f.x + (size_t)b0 * P; wa.err = f.err + (size_t)b0 * P; wa.mask = f.mask + (size_t)b0 * P;
+                wa.zabs = f.zabs + (size_t)b0 * Nb;
+                wa.Psi = f.Psi; wa.omega = f.omega;
+                wa.zero = reinterpret_cast<const uint8_t*>(g.PB + (size_t)nkb * (PB32_KB_BYTES / 4));   // 16 zero bytes after the image
+                wa.P = P; wa.Nb = Nb; wa.nkb = nkb; wa.nr = nr; wa.warp = warp; wa.lane = lane;
+                wa.git0 = git0;
+                wa.ring_sa = smem_u32(ring) + (uint32_t)warp * 1024u + (uint32_t)lane * 4u;
+                wa.bar_full = bar_full; wa.bar_empty = bar_empty;
+                wa.sE = sE + RPW * warp; wa.sNb = sNb + RPW * warp;
+                wa.trace = (kTrace && g.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && lane == 0) ? g.trace + warp * 4 : nullptr;
+                gram32_pass0_worker(wa, pc);
             }
             named_bar_sync(1, NTHREADS);            // sE / sNb visible; every worker is done with the ring
             // ----------------------------------------------------------- drain the accumulators (warps 0..3: lane = spectrum row)
