@@ -498,6 +498,33 @@ def test_tensor_core_nh32_train_path(cuda_model_factory):
             assert ge[k] < (5e-2 if k == "F" else 1e-2), k
 
 
+def test_tensor_core_nh32_ragged_batches():
+    """k_tc_gram32 / k_solve32 / k_tc_grad32 on batch sizes that exercise every ragged edge of their pipelines: fewer
+    spectra than one step of 3, fewer steps than ring stages (5) or TMEM buffers (2), fewer steps than CTAs per pixel
+    tile, a partial last tile of the Gram kernel (B % 120 != 0), B % 3 != 0.  Compared with the float CUDA-core path."""
+    from qfa_b200 import QFA, synth
+    grid = synth.GRIDS["l32"]
+    P, mu = synth.smooth_random_params(grid, 32, seed=77)
+    Pn = {k: v.numpy() for k, v in P.items()}
+    dev0 = torch.device("cuda:0")
+    ref = QFA(grid.Nb, grid.Nr, 32, dev0, model_params=Pn, precision="fp32")
+    tc = QFA(grid.Nb, grid.Nr, 32, dev0, model_params=Pn, precision="tf32")
+    dall = synth.make_spectra(P, mu, grid, 1300, seed=5, device=dev0, mask_iid=0.15, run_len=(40, 160))
+    for B in (1, 2, 3, 4, 5, 7, 16, 31, 121, 359, 1300):
+        a = [dall[k][:B].contiguous() for k in ("delta", "error", "zabs", "mask")]
+        n0 = torch.empty(B, device="cuda"); n1 = torch.empty(B, device="cuda")
+        ref.accumulate(*a, nll_out=n0); l0, g0 = ref.forward(*a)
+        tc.accumulate(*a, nll_out=n1); l1, g1 = tc.forward(*a)
+        npx = np.maximum(1, a[3].sum(1).cpu().numpy())
+        assert torch.isfinite(n1).all(), B
+        assert (np.abs((n1 - n0).cpu().numpy()) / npx).max() <= 1e-2, B
+        assert abs(float(l1) - float(l0)) <= 2e-3 * npx.mean(), B
+        for k in KEYS:
+            x, y = g1[k].cpu().numpy(), g0[k].cpu().numpy()
+            assert np.array_equal(np.isnan(x), np.isnan(y)), (B, k)          # 0/0 pixels (no unmasked spectrum) agree
+            assert relerr(x, y) < (0.25 if k == "F" else 5e-2), (B, k)       # few spectra: little averaging of TF32 noise
+
+
 # ----------------------------------------------------------------------------- device dataloader feeding QFA.train
 def test_device_dataloader_on_gpu_and_train(tmp_path):
     """DeviceDataloader on the GPU (delta through qfa_prepare_batch) == the same loader on the CPU (torch restatement of
