@@ -174,7 +174,7 @@ static TcPlan plan_tc(int Nb, int Nr, int B, bool want_qa, int quantum = 1) {
 }
 struct TcTrainPlan {
     TcPlan t;
-    int nchunks, nsplit, ntiles_blue;      // nsplit = max(ns_blue, ns_red): number of partial buffers
+    int nchunks, gct, nsplit, ntiles_blue;      // nsplit = max(ns_blue, ns_red): number of partial buffers
     int ns_blue, ns_red;
     size_t off_b2, off_kc, off_tsums, off_part, off_spart, total;
 };
@@ -182,7 +182,13 @@ static TcTrainPlan plan_tc_train(int Nb, int Nr, int Nh, int B) {
     TcTrainPlan p;
     const int P = Nb + Nr;
     p.t = plan_tc(Nb, Nr, B, true, 8);
-    p.nchunks = p.t.ntiles * tcg::GCT;
+    {   // chunks of GC spectra per tile: enough for the tallest tile of this launch (a 56-row tile has 3, not 5)
+        const int tall = p.t.ts.n_hi > 0 ? p.t.ts.r_hi : p.t.ts.r_lo;
+        p.gct = (tall + tcg::GC - 1) / tcg::GC;
+        if (p.gct < 1) p.gct = 1;
+        if (p.gct > tcg::GCT) p.gct = tcg::GCT;
+    }
+    p.nchunks = p.t.ntiles * p.gct;
     p.ntiles_blue = (Nb + tcg::PT - 1) / tcg::PT;
     if (p.ntiles_blue > p.t.npt) p.ntiles_blue = p.t.npt;
     {
@@ -404,7 +410,8 @@ static int train_accumulate_tc(const QfaModel* m, const float* delta, const floa
     static bool attr_done = false;
     if (!attr_done) {
         CK(cudaFuncSetAttribute(k_tc_gram<TC_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<TC_TRAIN>::SMEM_BYTES));
-        CK(cudaFuncSetAttribute(k_tc_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, GradSmem::BYTES));
+        CK(cudaFuncSetAttribute(k_tc_grad<GCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GradSmem::BYTES));
+        CK(cudaFuncSetAttribute(k_tc_grad<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GradSmem::BYTES));
         attr_done = true;
     }
     Field<float> f = make_field<float>(m, delta, error, zabs, mask);
@@ -416,12 +423,13 @@ static int train_accumulate_tc(const QfaModel* m, const float* delta, const floa
     k_tc_gram<TC_TRAIN><<<grid, NTHREADS, Cfg<TC_TRAIN>::SMEM_BYTES, st>>>(a);
     CK(cudaGetLastError());
     TcGradArgs ga;
-    ga.f = f; ga.B = B; ga.ts = pl.t.ts; ga.nchunks = pl.nchunks; ga.ns_blue = pl.ns_blue; ga.ns_red = pl.ns_red;
+    ga.f = f; ga.B = B; ga.ts = pl.t.ts; ga.nchunks = pl.nchunks; ga.gct = pl.gct; ga.ns_blue = pl.ns_blue; ga.ns_red = pl.ns_red;
     ga.ntiles_blue = pl.ntiles_blue; ga.npt = pl.t.npt; ga.QA = QA; ga.sm_b2 = sm_b2; ga.sm_kc = sm_kc;
     ga.zero = reinterpret_cast<const uint8_t*>(PB) + sw128_offset_host(36, 0);
     ga.part = part; ga.spart = spart; ga.accumulate = 0; ga.trace = g_trace_grad;
     const int grad_ctas = pl.ntiles_blue * pl.ns_blue + (pl.t.npt - pl.ntiles_blue) * pl.ns_red;
-    k_tc_grad<<<grad_ctas, GRAD_THREADS, GradSmem::BYTES, st>>>(ga);
+    if (pl.gct == GCT) k_tc_grad<GCT><<<grad_ctas, GRAD_THREADS, GradSmem::BYTES, st>>>(ga);
+    else k_tc_grad<0><<<grad_ctas, GRAD_THREADS, GradSmem::BYTES, st>>>(ga);
     CK(cudaGetLastError());
     ReduceArgs<float> ra;
     ra.part = part; ra.spart = spart; ra.nll = tsums; ra.hasblue = tsums + 1; ra.scal = f.scal;   // pre-folded per 32 rows
