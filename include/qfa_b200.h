@@ -36,7 +36,7 @@ extern "C" {
 /* precision modes */
 #define QFA_PREC_FP64 0 /* double everywhere; parity mode (<=1e-5 vs fp64-promoted reference) */
 #define QFA_PREC_FP32 1 /* float CUDA-core arithmetic (the reference itself is a float32 program) */
-#define QFA_PREC_TF32 2 /* "mixed": float everywhere; for batches >= QFA_TC_MIN_BATCH the contractions (weighted Grams,
+#define QFA_PREC_TF32 2 /* "mixed": float everywhere; above a per-path batch size (see QFA_FLAG_FORCE_TENSOR) the contractions (weighted Grams,
                            continuum/sigma, gradient) run on the tensor cores (tcgen05 kind::tf32, operands rounded to
                            TF32, fp32 accumulation in TMEM): Nh <= 8 train + predict, 8 < Nh <= 32 train */
 
@@ -49,7 +49,8 @@ extern "C" {
 /* flags */
 #define QFA_FLAG_ZERO_ACC 1     /* qfa_train_accumulate: clear `acc` before accumulating */
 #define QFA_FLAG_FORCE_TENSOR 2 /* QFA_PREC_TF32: use the tcgen05 kernels even for batches smaller than
-                                   QFA_TC_MIN_BATCH (env, default 1024) spectra */
+                                   the path's cross-over (predict 1280, train 512, train with
+                                   8 < Nh <= 32: 192 spectra; env QFA_TC_MIN_BATCH overrides) */
 #define QFA_FLAG_SOLVE_FP64 4   /* QFA_PREC_TF32, 8 < Nh <= 32: per-spectrum Cholesky in double instead of float (7 % slower
                                    train step; no measurable difference on any parity case, kept for ill-conditioned models) */
 

@@ -121,19 +121,23 @@ struct TcPlan {
     size_t off_pb, off_qa, total;
 };
 static inline bool tc_eligible(int Nh, int precision) { return precision == QFA_PREC_TF32 && Nh <= tcg::HP; }
-// The tensor-core kernels work on tiles of up to 128 spectra per CTA; below this batch size the float CUDA-core
-// kernels (one CTA per spectrum) fill the GPU better.  QFA_FLAG_FORCE_TENSOR overrides (tests, profiling).
-static int tc_min_batch() {
-    static int v = -1;
-    if (v < 0) {
+// The tensor-core kernels work on tiles of up to 120 spectra per CTA and have a latency floor of one pass over all K-blocks;
+// below a path-specific batch size the float CUDA-core kernels (one CTA per spectrum) are faster.  Measured cross-overs on a
+// B200 (profiles/r1_small_batch.txt): predict ~1 200 spectra, train step Nh <= 8 ~500, train step 8 < Nh <= 32 ~170.
+// QFA_TC_MIN_BATCH (env) overrides all three; QFA_FLAG_FORCE_TENSOR forces the tensor-core kernels (tests, profiling).
+enum { TC_PATH_PREDICT = 0, TC_PATH_TRAIN = 1, TC_PATH_TRAIN32 = 2 };
+static int tc_min_batch(int path) {
+    static int v = -2;
+    if (v == -2) {
         const char* s = getenv("QFA_TC_MIN_BATCH");
-        v = s ? atoi(s) : 1024;
-        if (v < 0) v = 0;
+        v = s ? atoi(s) : -1;
+        if (s && v < 0) v = 0;
     }
-    return v;
+    if (v >= 0) return v;
+    return path == TC_PATH_PREDICT ? 1280 : (path == TC_PATH_TRAIN ? 512 : 192);
 }
-static inline bool tc_use(int Nh, int precision, int B, int flags) {
-    return tc_eligible(Nh, precision) && (B >= tc_min_batch() || (flags & QFA_FLAG_FORCE_TENSOR));
+static inline bool tc_use(int Nh, int precision, int B, int flags, int path) {
+    return tc_eligible(Nh, precision) && (B >= tc_min_batch(path) || (flags & QFA_FLAG_FORCE_TENSOR));
 }
 
 // Tile heights: the tile count should be a whole number of waves of num_sms() persistent CTAs.  Heights are
@@ -509,14 +513,14 @@ extern "C" int qfa_train_accumulate(const QfaModel* model, const float* delta, c
         return fail(QFA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total, workspace_bytes);
     if (((uintptr_t)workspace & 255) != 0) return fail(QFA_ERR_ALIGN, "workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    if (tc_use(model->Nh, precision, B, flags)) {
+    if (tc_use(model->Nh, precision, B, flags, TC_PATH_TRAIN)) {
         TcTrainPlan tp = plan_tc_train(model->Nb, model->Nr, model->Nh, B);
         if (B > 0 && workspace_bytes < tp.total)
             return fail(QFA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", tp.total, workspace_bytes);
         return train_accumulate_tc(model, delta, error, zabs, mask, B, (char*)workspace, tp, (float*)acc,
                                    (float*)nll_per_spectrum, flags, st);
     }
-    if (tc32_eligible(model->Nh, precision) && (B >= tc_min_batch() || (flags & QFA_FLAG_FORCE_TENSOR))) {
+    if (tc32_eligible(model->Nh, precision) && (B >= tc_min_batch(TC_PATH_TRAIN32) || (flags & QFA_FLAG_FORCE_TENSOR))) {
         Tc32Plan tp = plan_tc32(model->Nb, model->Nr, model->Nh, B);
         if (B > 0 && workspace_bytes < tp.total)
             return fail(QFA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", tp.total, workspace_bytes);
@@ -583,7 +587,7 @@ extern "C" int qfa_predict(const QfaModel* model, const float* flux, const float
     if (!nll) return fail(QFA_ERR_NULL, "nll is NULL");
     if (!flux || !error || !mask || (!zabs && model->Nb > 0)) return fail(QFA_ERR_NULL, "flux/error/zabs/mask is NULL");
     cudaStream_t st = (cudaStream_t)stream;
-    if (tc_use(model->Nh, precision, B, flags)) {
+    if (tc_use(model->Nh, precision, B, flags, TC_PATH_PREDICT)) {
         const bool want_o = cont || unc;
         TcPlan pl = plan_tc(model->Nb, model->Nr, B, true);
         if (!workspace || workspace_bytes < pl.total)

@@ -11,7 +11,7 @@ d = synth.make_spectra(P, mu, grid, 8192, seed=1, device=dev)
 for prec in ("mixed", "tf32"):
     m = QFA(grid.Nb, grid.Nr, 8, dev, model_params={a: b.numpy() for a, b in P.items()}, precision=prec); m.mu = mu
     opt = Adam(params=m.parameters, device=dev, scheduler=step_scheduler(0.9, 10), learning_rate=1e-3, weight_decay=0.1)
-    for B in (500, 1024, 2048, 8192):
+    for B in ([int(a) for a in sys.argv[1:]] or [500, 1024, 2048, 8192]):
         X, E, Z, M = d["delta"][:B], d["error"][:B], d["zabs"][:B], d["mask"][:B].view(torch.uint8)
         def step():
             acc = m.accumulate(X, E, Z, M, zero=True)
