@@ -183,8 +183,8 @@ __device__ __noinline__ void gram32_pass0_worker(const G32Worker w, const PhysCo
         constexpr bool PASS0 = true;
         auto load_kb = [&](int kb, KBuf& k) {
             const int p0 = kb * KB;
-            if (p0 + KB <= P) load_kblock<true, true, NR>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
-            else load_kblock<true, false, NR>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
+            if (p0 + KB <= P) load_kblock<true, true, NR, true, true>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
+            else load_kblock<true, false, NR, true, true>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
         };
         load_kb(0, kA);
         if (nkb > 1) load_kb(1, kB);
