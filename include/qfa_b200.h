@@ -180,6 +180,15 @@ int qfa_selftest_umma(const float* A, const float* Bimg_hi, const float* Bimg_lo
                       int* err_flag, void* stream);
 
 /*
+ * Self-test of a 2-D TMA tile load (cp.async.bulk.tensor.2d through a tensor map encoded at run time) from a pitched
+ * row-major float array src[rows][pitch_px] with npix valid pixels per row: out[120][32] = the box starting at row y0,
+ * pixel x0 (out-of-range elements = 0).  pitch_px * 4 must be a multiple of 16 (QFA_ERR_ALIGN otherwise: this is exactly
+ * why the dense reference layout with odd Npix cannot use TMA).  Test-only entry point.
+ */
+int qfa_selftest_tma2d(const float* src, int rows, int npix, int pitch_px, int x0, int y0, float* out, int* err_flag,
+                       void* stream);
+
+/*
  * Debug/profiling aid: `device_buffer` (long long[nkb * 16 * 4], or NULL to switch off) receives clock64 stamps of
  * the first tile of CTA 0 of every following k_tc_gram launch: per K-block and warp {enter, stage free, operands
  * written, done}.  Not part of the reference-facing surface.

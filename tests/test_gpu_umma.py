@@ -50,3 +50,28 @@ def test_umma_selftest(split):
     if not split:   # and the plain product really is TF32: matches the rounded-operand product much tighter
         ref_tf = tf32_round(A).astype(np.float64) @ Bhi.astype(np.float64).T
         assert np.abs(got[:, :48] - ref_tf).max() < 2e-5 * np.abs(ref).max()
+
+
+def test_tma2d_selftest_pitched_rows():
+    """2-D TMA box loads from a padded-pitch float array (the building block of the planned TMA input path): interior box,
+    a box that hangs over the right edge (pixels >= npix arrive as 0) and over the last row; and the dense odd-pitch layout
+    of the reference (1913 floats per row) is rejected, which is why today's kernels load per thread."""
+    from qfa_b200 import _lib
+    L = _lib.lib()
+    rows, npix, pitch = 300, 1913, 1920
+    src = torch.arange(rows * pitch, dtype=torch.float32, device="cuda").reshape(rows, pitch)
+    out = torch.empty(120, 32, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    for x0, y0 in ((64, 8), (1900, 0), (32, 250)):
+        out.fill_(-1.0)
+        _lib.check(L.qfa_selftest_tma2d(p(src), rows, npix, pitch, x0, y0, p(out), p(err), None), "qfa_selftest_tma2d")
+        torch.cuda.synchronize()
+        assert int(err.item()) == 0
+        ref = torch.zeros(120, 32, device="cuda")
+        r1, c1 = min(rows, y0 + 120), min(npix, x0 + 32)
+        ref[:r1 - y0, :c1 - x0] = src[y0:r1, x0:c1]
+        assert torch.equal(out, ref), (x0, y0)
+    dense = torch.zeros(rows * npix, device="cuda")
+    assert L.qfa_selftest_tma2d(p(dense), rows, npix, npix, 0, 0, p(out), p(err), None) == -6      # QFA_ERR_ALIGN
+
