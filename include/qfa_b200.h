@@ -188,6 +188,10 @@ int qfa_selftest_umma(const float* A, const float* Bimg_hi, const float* Bimg_lo
 int qfa_selftest_tma2d(const float* src, int rows, int npix, int pitch_px, int x0, int y0, float* out, int* err_flag,
                        void* stream);
 
+/* Streaming micro-benchmark of the same TMA tile path: one persistent kernel reads src[rows][pitch_px] once through 4-stage
+ * rings of 120 x box_w boxes (box_w = 32, 64 or 128).  The caller times it.  Test / design aid. */
+int qfa_bench_tma2d(const float* src, int rows, int npix, int pitch_px, int box_w, float* sink, int* err_flag, void* stream);
+
 /*
  * Debug/profiling aid: `device_buffer` (long long[nkb * 16 * 4], or NULL to switch off) receives clock64 stamps of
  * the first tile of CTA 0 of every following k_tc_gram launch: per K-block and warp {enter, stage free, operands

@@ -795,12 +795,7 @@ extern "C" int qfa_selftest_umma(const float* A, const float* Bimg_hi, const flo
 
 // 2-D TMA tile load from a pitched array (see qfa_tc_selftest.cuh).  The tensor-map encoder lives in the driver: it is
 // fetched at run time, the library does not link libcuda.
-extern "C" int qfa_selftest_tma2d(const float* src, int rows, int npix, int pitch_px, int x0, int y0, float* out,
-                                  int* err_flag, void* stream) {
-    if (!src || !out || !err_flag) return fail(QFA_ERR_NULL, "NULL argument");
-    if (rows <= 0 || npix <= 0 || pitch_px < npix) return fail(QFA_ERR_SHAPE, "rows=%d npix=%d pitch=%d", rows, npix, pitch_px);
-    if ((pitch_px * 4) % 16 != 0 || ((uintptr_t)src & 15) != 0)
-        return fail(QFA_ERR_ALIGN, "a tensor map needs a 16-byte aligned base and a row pitch that is a multiple of 16 bytes");
+static int encode_tile_map(CUtensorMap* tm, const float* src, int rows, int npix, int pitch_px, int box_w, int box_h) {
     typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -808,16 +803,49 @@ extern "C" int qfa_selftest_tma2d(const float* src, int rows, int npix, int pitc
     cudaDriverEntryPointQueryResult qres;
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) return fail(QFA_ERR_SHAPE, "cuTensorMapEncodeTiled is not available");
-    CUtensorMap tm;
     const cuuint64_t gdim[2] = {(cuuint64_t)npix, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)pitch_px * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)TMA_ST_COLS, (cuuint32_t)TMA_ST_ROWS};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = ((EncodeTiled)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)src, gdim, gstride, box, estr,
+    const CUresult r = ((EncodeTiled)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)src, gdim, gstride, box, estr,
                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(QFA_ERR_SHAPE, "cuTensorMapEncodeTiled failed: %d", (int)r);
+    return 0;
+}
+extern "C" int qfa_selftest_tma2d(const float* src, int rows, int npix, int pitch_px, int x0, int y0, float* out,
+                                  int* err_flag, void* stream) {
+    if (!src || !out || !err_flag) return fail(QFA_ERR_NULL, "NULL argument");
+    if (rows <= 0 || npix <= 0 || pitch_px < npix) return fail(QFA_ERR_SHAPE, "rows=%d npix=%d pitch=%d", rows, npix, pitch_px);
+    if ((pitch_px * 4) % 16 != 0 || ((uintptr_t)src & 15) != 0)
+        return fail(QFA_ERR_ALIGN, "a tensor map needs a 16-byte aligned base and a row pitch that is a multiple of 16 bytes");
+    CUtensorMap tm;
+    if (int rc = encode_tile_map(&tm, src, rows, npix, pitch_px, TMA_ST_COLS, TMA_ST_ROWS)) return rc;
     k_selftest_tma2d<<<1, 128, 0, (cudaStream_t)stream>>>(tm, out, x0, y0, err_flag);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Streaming micro-benchmark of the TMA tile path (see k_bench_tma2d): reads src[rows][pitch_px] once, box_w = 32 | 64 | 128.
+extern "C" int qfa_bench_tma2d(const float* src, int rows, int npix, int pitch_px, int box_w, float* sink, int* err_flag,
+                               void* stream) {
+    if (!src || !sink || !err_flag) return fail(QFA_ERR_NULL, "NULL argument");
+    if (rows <= 0 || npix <= 0 || pitch_px < npix) return fail(QFA_ERR_SHAPE, "rows=%d npix=%d pitch=%d", rows, npix, pitch_px);
+    if ((pitch_px * 4) % 16 != 0 || ((uintptr_t)src & 15) != 0) return fail(QFA_ERR_ALIGN, "pitch / base alignment");
+    CUtensorMap tm;
+    if (int rc = encode_tile_map(&tm, src, rows, npix, pitch_px, box_w, TMA_ST_ROWS)) return rc;
+    const int smem = (box_w >= 128 ? 3 : 4) * TMA_ST_ROWS * box_w * 4 + 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (box_w == 32) {
+        CK(cudaFuncSetAttribute(k_bench_tma2d<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_bench_tma2d<32><<<num_sms(), 256, smem, st>>>(tm, rows, npix, sink, err_flag);
+    } else if (box_w == 64) {
+        CK(cudaFuncSetAttribute(k_bench_tma2d<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_bench_tma2d<64><<<num_sms(), 256, smem, st>>>(tm, rows, npix, sink, err_flag);
+    } else if (box_w == 128) {
+        CK(cudaFuncSetAttribute(k_bench_tma2d<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_bench_tma2d<128><<<num_sms(), 256, smem, st>>>(tm, rows, npix, sink, err_flag);
+    } else return fail(QFA_ERR_SHAPE, "box_w must be 32, 64 or 128");
     CK(cudaGetLastError());
     return 0;
 }
