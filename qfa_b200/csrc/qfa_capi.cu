@@ -807,9 +807,16 @@ static int encode_tile_map(CUtensorMap* tm, const float* src, int rows, int npix
     const cuuint64_t gstride[1] = {(cuuint64_t)pitch_px * 4};
     const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
     const cuuint32_t estr[2] = {1, 1};
+    // QFA_TMA_L2PROMO = 0 | 64 | 128 | 256 (design experiments: L2 promotion size of the tensor map)
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    if (const char* e = getenv("QFA_TMA_L2PROMO")) {
+        const int v = atoi(e);
+        promo = v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+              : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    }
     const CUresult r = ((EncodeTiled)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)src, gdim, gstride, box, estr,
-                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(QFA_ERR_SHAPE, "cuTensorMapEncodeTiled failed: %d", (int)r);
     return 0;
 }
@@ -834,7 +841,7 @@ extern "C" int qfa_bench_tma2d(const float* src, int rows, int npix, int pitch_p
     if ((pitch_px * 4) % 16 != 0 || ((uintptr_t)src & 15) != 0) return fail(QFA_ERR_ALIGN, "pitch / base alignment");
     CUtensorMap tm;
     if (int rc = encode_tile_map(&tm, src, rows, npix, pitch_px, box_w, TMA_ST_ROWS)) return rc;
-    const int smem = (box_w >= 128 ? 3 : 4) * TMA_ST_ROWS * box_w * 4 + 128;
+    const int smem = (box_w >= 128 ? 3 : (box_w == 64 ? 4 : QFA_TMA_NST32)) * TMA_ST_ROWS * box_w * 4 + 128;
     cudaStream_t st = (cudaStream_t)stream;
     if (box_w == 32) {
         CK(cudaFuncSetAttribute(k_bench_tma2d<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
