@@ -192,6 +192,10 @@ int qfa_selftest_tma2d(const float* src, int rows, int npix, int pitch_px, int x
  * rings of 120 x box_w boxes (box_w = 32, 64 or 128).  The caller times it.  Test / design aid. */
 int qfa_bench_tma2d(const float* src, int rows, int npix, int pitch_px, int box_w, float* sink, int* err_flag, void* stream);
 
+/* ... and through the per-thread loader pattern of the production kernels (15 warps x 8 rows, 128-byte row segments, two
+ * register buffers), any pitch.  Test / design aid. */
+int qfa_bench_ldg(const float* src, int rows, int npix, int pitch_px, float* sink, void* stream);
+
 /*
  * Debug/profiling aid: `device_buffer` (long long[nkb * 16 * 4], or NULL to switch off) receives clock64 stamps of
  * the first tile of CTA 0 of every following k_tc_gram launch: per K-block and warp {enter, stage free, operands

@@ -85,6 +85,7 @@ SIGNATURES = {
     "qfa_selftest_umma": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP]),
     "qfa_selftest_tma2d": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP, _VP]),
     "qfa_bench_tma2d": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP]),
+    "qfa_bench_ldg": (_I, [_VP, _I, _I, _I, _VP, _VP]),
     "qfa_debug_set_trace": (_I, [_VP]),
     "qfa_debug_set_trace_grad": (_I, [_VP]),
 }

@@ -856,3 +856,12 @@ extern "C" int qfa_bench_tma2d(const float* src, int rows, int npix, int pitch_p
     CK(cudaGetLastError());
     return 0;
 }
+
+// The same stream with the per-thread loader pattern of the production kernels (see k_bench_ldg); any pitch.
+extern "C" int qfa_bench_ldg(const float* src, int rows, int npix, int pitch_px, float* sink, void* stream) {
+    if (!src || !sink) return fail(QFA_ERR_NULL, "NULL argument");
+    if (rows <= 0 || npix <= 0 || pitch_px < npix) return fail(QFA_ERR_SHAPE, "rows=%d npix=%d pitch=%d", rows, npix, pitch_px);
+    k_bench_ldg<<<num_sms(), 512, 0, (cudaStream_t)stream>>>(src, rows, npix, pitch_px, sink);
+    CK(cudaGetLastError());
+    return 0;
+}

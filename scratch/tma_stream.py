@@ -16,3 +16,14 @@ for bw in (32, 64, 128):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     print(f"box {bw:3d} px: {ms:.3f} ms  {rows*npix*4/ms/1e6:.0f} GB/s of payload  (err flag {int(err.item())})")
+for name, pit in (("dense pitch 1913", 1913), ("padded pitch 1920", 1920)):
+    a = torch.randn(rows, pit, device="cuda")
+    for _ in range(2): _lib.check(L.qfa_bench_ldg(p(a), rows, npix, pit, p(sink), None), "ldg")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): _lib.check(L.qfa_bench_ldg(p(a), rows, npix, pit, p(sink), None), "ldg")
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"per-thread loads, {name}: {ms:.3f} ms  {rows*(npix//32*32)*4/ms/1e6:.0f} GB/s of payload")
+
