@@ -1,26 +1,30 @@
 #!/usr/bin/env python
-"""bench.py -- throughput of the QFA hot path on B200 (contract: see the task statement / DESIGN.md).
+"""bench.py -- throughput of the QFA hot path on B200 (contract: see the task statement / DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--precision P]
 
-One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of
-synthetic spectra:
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of synthetic spectra.
 
-  workload sdss100k_predict (default; BASELINE.json configs[1]): batched log-likelihood +
-      posterior continuum inference of 100 000 SDSS-shaped spectra (Npix 1913 / Nb 720) with the
-      pretrained Nh=8 model, per GPU (weak scaling: every rank owns its own 100k spectra, no
-      collective on the data path).
-  `also` (reported inside the same line): the likelihood+gradient train step of configs[3]
-      (SDSS shape, Nh=8) and configs[4] (Npix 1000, Nh=32, 30 % masked), data-parallel with ONE
-      all-reduce of the packed accumulation buffer per step.
+  headline at N = 1:  sdss100k_predict (BASELINE.json configs[1]) -- batched log-likelihood + posterior continuum
+      inference of 100 000 SDSS-shaped spectra (Npix 1913 / Nb 720) with the pretrained Nh = 8 model.
+  headline at N > 1:  sdss_train (configs[3]) -- the likelihood + gradient train step, data parallel with ONE NCCL
+      all-reduce of the packed accumulation buffer per step, so that the driver's 1 -> 8 curve sees the collective
+      (predict / scoring shard with no collective at all: their efficiency is 1.0 by construction).  The N = 1 value
+      of the SAME workload is `also.sdss_train.value` of the N = 1 line.
+  `also` (same line, every entry with its own clocks / e2e / cpu_baseline / launch count):
+      sdss_train, l32_train (configs[4]: Npix 1000, Nh 32, 30 % masked), desi_score (configs[2]: NLL-only scoring + on-device
+      top-k), sdss_train_b8192 and sdss_train_b500 (configs[3] at 8192 spectra per GPU and at the reference's global batch of
+      500: the WHOLE step -- shuffled gather + delta, accumulate, all-reduce, Adam+clip -- replayed as one CUDA graph),
+      sdss_train_tf32x3 (3xTF32 operands).
 
-`value` is spectra/s with the inputs resident in HBM; `e2e` is the same metric through the
-reference-shaped Python API with HOST (pinned) buffers, H2D/D2H copies inside the timed region.
+`value` is spectra/s with the inputs resident in HBM; `e2e` is the same metric through the reference-shaped Python API
+with HOST (pinned) buffers, H2D/D2H copies inside the timed region.  `gpu_launches` is counted by the library
+(qfa_launch_count), not assumed.  `--impl reference` times the UNMODIFIED reference (baseline/_ref, pip --target install)
+when it is present, else the dense CPU port in oracle/, on a bounded sample of the same workload, honouring --steps/--warmup.
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -38,33 +42,30 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sdss100k_predict",
-                    choices=["sdss100k_predict", "sdss_train", "l32_train", "desi_score"])
-    ap.add_argument("--precision", default="mixed", choices=["mixed", "fp32", "fp64"])
+    ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "tf32", "tf32x3", "fp32", "fp64"])
     ap.add_argument("--spectra", type=int, default=0, help="spectra per GPU per step (0 = workload default)")
-    ap.add_argument("--no-also", action="store_true", help="skip the secondary (train-step) measurements")
+    ap.add_argument("--also", default="default", help="comma list of secondary workloads, 'default' or 'none'")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
+# name: grid, Nh, kind, spectra per GPU per step, CPU sample (spectra per CPU step), BASELINE.json config, extras
 WORKLOADS = {
-    # name: (grid, Nh, kind, default spectra per GPU, cpu sample)
-    "sdss100k_predict": ("sdss", 8, "predict", 100_000, 192),
-    "sdss_train": ("sdss", 8, "train", 71_040, 64),        # 148 SMs x 4 waves x 120-spectra tiles
-    "l32_train": ("l32", 32, "train", 65_536, 256),
-    "desi_score": ("desi", 8, "score", 32_768, 4),
+    "sdss100k_predict": dict(grid="sdss", Nh=8, kind="predict", nspec=100_000, sample=192, baseline_config=1),
+    "sdss_train": dict(grid="sdss", Nh=8, kind="train", nspec=71_040, sample=64, baseline_config=3),   # 148 SMs x 4 x 120
+    "l32_train": dict(grid="l32", Nh=32, kind="train", nspec=65_536, sample=256, baseline_config=4),
+    "desi_score": dict(grid="desi", Nh=8, kind="score", nspec=32_768, sample=4, baseline_config=2),
+    "sdss_train_b8192": dict(grid="sdss", Nh=8, kind="graph_train", nspec=8192, sample=64, baseline_config=3),
+    "sdss_train_b500": dict(grid="sdss", Nh=8, kind="graph_train", nspec=500, sample=64, baseline_config=3,
+                            global_batch=500),
+    "sdss_train_tf32x3": dict(grid="sdss", Nh=8, kind="train", nspec=71_040, sample=64, baseline_config=3,
+                              precision="tf32x3"),
 }
-
-
-def measured_traffic(kind, grid_name, Nh, nspec):
-    """DRAM bytes per launch of the dominant kernel, scaled from the committed `ncu --set full` capture
-    (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per spectrum of that capture)."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        return t[f"{kind}_{grid_name}_nh{Nh}"]["dram_bytes_per_spectrum"] * nspec
-    except Exception:
-        return None
+DEFAULT_ALSO = {1: ["sdss_train", "l32_train", "desi_score", "sdss_train_b8192", "sdss_train_b500", "sdss_train_tf32x3"],
+                0: ["l32_train", "sdss_train_b8192", "sdss_train_b500"]}     # 0 = any N > 1
 
 
 def bytes_per_spectrum(kind, P, Nb, Nh):
@@ -72,6 +73,19 @@ def bytes_per_spectrum(kind, P, Nb, Nh):
     if kind == "predict":
         return 17 * P + 4 * Nb + 4 * Nh * Nh + 4 * Nh + 4
     return 9 * P + 4 * Nb + 4
+
+
+def committed_traffic(kind, grid_name, Nh, nspec):
+    """DRAM bytes per launch of the dominant kernel, SCALED from the committed `ncu --set full` capture of the same kernel
+    (profiles/r2_traffic.json, else r1): dram__bytes_read.sum + dram__bytes_write.sum per spectrum of that capture x spectra."""
+    for f in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", f)))
+            k = "train" if kind in ("train", "graph_train") else kind
+            return t[f"{k}_{grid_name}_nh{Nh}"]["dram_bytes_per_spectrum"] * nspec, f"profiles/{f} (committed ncu capture, scaled)"
+        except Exception:
+            continue
+    return None, None
 
 
 def model_and_params(grid_name, Nh):
@@ -92,9 +106,26 @@ def model_and_params(grid_name, Nh):
     return grid, P, mu
 
 
+def workload_config(name, nspec, precision, world=1):
+    w = WORKLOADS[name]
+    from qfa_b200 import synth
+    grid = synth.GRIDS[w["grid"]]
+    kind = w["kind"]
+    cfg = {"workload": name, "baseline_config": "BASELINE.json configs[%d]" % w["baseline_config"],
+           "kind": "train" if kind == "graph_train" else kind, "grid": w["grid"], "Npix": grid.Npix, "Nb": grid.Nb,
+           "Nh": w["Nh"], "spectra_per_gpu_per_step": nspec, "precision": w.get("precision", precision),
+           "l2": "inputs per step exceed L2 (%.0f MB)" % (nspec * (9 * grid.Npix + 4 * grid.Nb) / 1e6)
+           if nspec * (9 * grid.Npix + 4 * grid.Nb) > 126e6 else
+           "a NEW batch is gathered from the HBM-resident data set every step (shuffled rows; the data set exceeds L2)"}
+    if kind == "graph_train":
+        cfg["step"] = "one CUDA-graph replay: gather+delta of a shuffled batch, accumulate, all-reduce, Adam+clip"
+        cfg["global_batch"] = w.get("global_batch", nspec * world)
+    return cfg
+
+
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region.  The timed region of the default run is ~10 ms, far
-    shorter than nvidia-smi's sampling period, so NVML is polled directly from a thread (every ~1 ms)."""
+    """SM clock and throttle reasons DURING the timed region.  The timed regions are ~10 ms, far shorter than nvidia-smi's
+    sampling period, so NVML is polled directly from a thread (every ~1 ms)."""
 
     def __init__(self, index):
         self.rows, self.ok, self.stop_flag = [], False, False
@@ -163,6 +194,40 @@ def emit(obj):
         os.write(_REAL_STDOUT, data)
 
 
+def bind_to_gpu_numa(local):
+    """Pin this rank's host threads (and, by first touch, its pinned staging buffers) to the CPUs next to its GPU.  Round 1
+    ran all 8 ranks on NUMA node 0 (`CPU Affinity 0-31`), so every rank's H2D/D2H crossed the same host memory
+    controller and the end-to-end numbers did not scale (SCALE_r01: 0.22 at N = 8)."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local]) if vis and vis.split(",")[local].isdigit() else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * wi + b for wi, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        info.update(gpu_cpus=len(cpus), allowed_before=len(allowed))
+        try:
+            os.sched_setaffinity(0, cpus)              # the GPU's node, even if the launcher pinned us elsewhere
+            info.update(bound=True, cpus=len(cpus))
+        except OSError:
+            both = cpus & allowed
+            if both:
+                os.sched_setaffinity(0, both)
+                info.update(bound=True, cpus=len(both))
+        try:
+            info["numa_node"] = int(open("/sys/bus/pci/devices/%s/numa_node" %
+                                         pynvml.nvmlDeviceGetPciInfo(h).busId.decode().lower()[-12:]).read())
+        except Exception:
+            pass
+    except Exception as e:           # binding is an optimisation, never a failure
+        info["error"] = str(e)[:80]
+    return info
+
+
 def dist_setup(n):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -204,158 +269,282 @@ def timed(fn, steps, warmup, world):
     return ms, t0, t1
 
 
-# ----------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_reference_run(workload, steps, warmup, sample):
-    """Times the dense CPU port of the reference algorithm (oracle/qfa_dense.py -- the reference itself
-    is pure Python and does not travel to the GPU box) on all host cores."""
-    from oracle import qfa_dense
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_run(name, steps, warmup):
+    """The reference's CPU implementation of the workload on all host cores, on a bounded sample (`sample` spectra per step)
+    of the same synthetic data: the UNMODIFIED reference (pip --target install under baseline/_ref, or $QFA_REF) through
+    its own public API when it is importable -- QFA.forward (model.py:74-105) for the train step,
+    prediction_for_single_spectra (model.py:160-180) per spectrum for predict / scoring, exactly the loops of
+    model.py:210-214 and main.py:94-95 -- else the dense port oracle/qfa_dense.py."""
     from qfa_b200 import synth
-    grid_name, Nh, kind, _, _ = WORKLOADS[workload]
+    w = WORKLOADS[name]
+    grid_name, Nh, kind, sample = w["grid"], w["Nh"], w["kind"], w["sample"]
     grid, P, mu = model_and_params(grid_name, Nh)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     kw = dict(mask_iid=0.15, run_len=(40, 160)) if grid_name == "l32" else {}
     d = synth.make_spectra(P, mu, grid, sample, seed=1234, **kw)
+    from oracle import ref_loader
+    root = ref_loader.find_reference()
+    train = kind in ("train", "graph_train")
+    if root is not None:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            RQFA, _, _, _ = ref_loader.load_reference(root=root)
+        cpu = torch.device("cpu")
+        m = RQFA(grid.Nb, grid.Nr, Nh, cpu)
+        m.F, m.Psi, m.omega = P["F"].clone(), P["Psi"].clone(), P["omega"].clone()
+        m.tau0, m.c0, m.beta = P["tau0"].clone(), P["c0"].clone(), P["beta"].clone()
+        m.mu = mu.clone()
+        kind_s = "reference"
 
-    def step():
-        if kind == "train":
-            qfa_dense.forward(P, d["delta"], d["error"], d["zabs"], d["mask"], grid.Nb)
-        else:
-            for b in range(sample):
-                qfa_dense.predict_single(P, mu, d["flux"][b], d["error"][b], d["zabs"][b], d["mask"][b], grid.Nb)
+        def step():
+            if train:
+                m.forward(d["delta"], d["error"], d["zabs"], d["mask"])
+            else:
+                for b in range(sample):
+                    m.prediction_for_single_spectra(d["flux"][b], d["error"][b], d["zabs"][b], d["mask"][b])
+    else:
+        from oracle import qfa_dense
+        kind_s = "port"
+
+        def step():
+            if train:
+                qfa_dense.forward(P, d["delta"], d["error"], d["zabs"], d["mask"], grid.Nb)
+            else:
+                for b in range(sample):
+                    qfa_dense.predict_single(P, mu, d["flux"][b], d["error"][b], d["zabs"][b], d["mask"][b], grid.Nb)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return sample * steps / dt, dt / steps * 1e3, cores, f"{sample} spectra/step of the {workload} workload (seed 1234)"
+    desc = (f"{sample} spectra/step of the {name} workload (seed 1234), {steps} step(s) after {warmup} warm-up; "
+            + ("unmodified reference from " + os.path.relpath(root, ROOT) if root else "dense port oracle/qfa_dense.py"))
+    return {"value": sample * steps / dt, "unit": "spectra/s", "cores": cores, "kind": kind_s, "sample": desc}, dt / steps * 1e3
+
+
+def headline_for(n_gpus, requested):
+    if requested != "auto":
+        return requested
+    return "sdss100k_predict" if n_gpus <= 1 else "sdss_train"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    grid_name, Nh, kind, nspec, sample = WORKLOADS[args.workload]
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    v, ms, cores, desc = cpu_reference_run(args.workload, steps, warmup, sample)
-    line = {"impl": "reference", "metric": "spectra/sec", "value": v, "unit": "spectra/s", "n_gpus": args.gpus,
+    name = headline_for(args.gpus, args.workload)
+    w = WORKLOADS[name]
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    cb, ms = cpu_run(name, steps, warmup)
+    line = {"impl": "reference", "metric": "spectra/sec", "value": cb["value"], "unit": "spectra/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "kind": kind, "grid": grid_name, "Nh": Nh},
-            "cpu_baseline": {"value": v, "unit": "spectra/s", "cores": cores, "kind": "port", "sample": desc},
-            "e2e": {"value": v, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "config": workload_config(name, args.spectra or w["nspec"], args.precision, max(1, args.gpus)),
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def kernel_names(kind, Nh, precision):
+    tc = precision in ("mixed", "tf32", "tf32x3")
+    if kind in ("train", "graph_train"):
+        if tc and Nh <= 8:
+            return "k_tc_gram<TRAIN> + k_tc_grad (tcgen05) + k_reduce + k_adam"
+        if tc and Nh <= 32:
+            return "k_tc_gram32 + k_solve32 + k_tc_grad32 (tcgen05) + k_reduce + k_adam"
+        return "k_gram_solve + k_grad (CUDA cores) + k_reduce + k_adam"
+    if tc and Nh <= 8:
+        return "k_tc_gram<PREDICT> (tcgen05 Gram GEMM + solve + continuum GEMM)"
+    return "k_gram_solve (CUDA cores)"
+
+
 def measure_workload(name, args, rank, world, peaks, want_e2e, want_cpu, nspec_override=0):
-    from qfa_b200 import QFA, Adam, step_scheduler, synth
-    grid_name, Nh, kind, nspec, sample = WORKLOADS[name]
+    from qfa_b200 import QFA, Adam, step_scheduler, synth, DeviceDataloader, _lib
+    w = WORKLOADS[name]
+    grid_name, Nh, kind, nspec = w["grid"], w["Nh"], w["kind"], w["nspec"]
+    precision = w.get("precision", args.precision)
     if nspec_override:
         nspec = nspec_override
+    if kind == "graph_train" and "global_batch" in w:
+        nspec = max(1, w["global_batch"] // world)          # strong scaling of the reference's batch of 500
     grid, P, mu = model_and_params(grid_name, Nh)
     dev = torch.device("cuda", torch.cuda.current_device())
     Pn = {k: v.numpy() for k, v in P.items()}
-    m = QFA(grid.Nb, grid.Nr, Nh, dev, model_params=Pn, precision=args.precision)
+    m = QFA(grid.Nb, grid.Nr, Nh, dev, model_params=Pn, precision=precision)
     m.mu = mu
     if world > 1:
         m.enable_data_parallel()
     kw = dict(mask_iid=0.15, run_len=(40, 160)) if grid_name == "l32" else {}
     ood = 0.01 if kind == "score" else 0.0
-    d = synth.make_spectra(P, mu, grid, nspec, seed=1234 + rank, device=dev, ood_frac=ood, **kw)
-    X = d["delta"] if kind == "train" else d["flux"]
-    E, Z, M = d["error"], d["zabs"], d["mask"].view(torch.uint8)
-    launches = [0]
+    L = _lib.lib()
     res = {}
+    steps = args.steps
+    if kind == "graph_train":
+        # the data set: enough fresh rows for every timed step, at most ~1.6 GB; the cursor wraps by an in-stream reset
+        rows = min(nspec * (steps + args.warmup), max(nspec, 81_920))
+        d = synth.make_spectra(P, mu, grid, rows, seed=1234 + rank, device=dev, **kw)
+        wav = grid.wav()
+        dl = DeviceDataloader(d["flux"], d["error"], d["zqso"], d["mask"], wav, batch_size=nspec, device=dev,
+                              shuffle=True, seed=5)      # rank-local loader: nspec rows per rank and step
+        dl.data_size = rows * world
+        del d
+        opt = Adam(params=m.parameters, device=dev, scheduler=step_scheduler(0.9, 10), learning_rate=1e-3, weight_decay=0.1)
+        p0 = m._params.clone()
+        dl.rewind()
+        g = m.capture_train_step(opt, dl, max(1, rows // nspec))
+        per_epoch = rows // nspec
+        state = {"n": 0}
+
+        def step():
+            if state["n"] % per_epoch == 0:
+                dl._cursor.zero_()
+            g.replay()
+            state["n"] += 1
+        launches_per_step = m.graph_launches_per_step
+        X = E = Z = M = None
+    else:
+        d = synth.make_spectra(P, mu, grid, nspec, seed=1234 + rank, device=dev, ood_frac=ood, **kw)
+        X = d["delta"] if kind == "train" else d["flux"]
+        E, Z, M = d["error"], d["zabs"], d["mask"].view(torch.uint8)
     if kind == "train":
-        opt = Adam(params=m.parameters, device=dev, scheduler=step_scheduler(0.9, 10), learning_rate=1e-3,
-                   weight_decay=0.1)
+        opt = Adam(params=m.parameters, device=dev, scheduler=step_scheduler(0.9, 10), learning_rate=1e-3, weight_decay=0.1)
         p0 = m._params.clone()
 
         def step():
             acc = m.accumulate(X, E, Z, M, zero=True)
             m._allreduce(acc)
             opt.update_from_acc(m, acc)
-        if Nh <= 8 and args.precision == "mixed":
-            # k_tc_build_images, k_tc_gram<TRAIN>, k_tc_grad, k_reduce, k_adam
-            launches_per_step = 5
-            kernel_name = "k_tc_gram<TRAIN> + k_tc_grad (tcgen05) + k_reduce + k_adam"
-        elif 8 < Nh <= 32 and args.precision == "mixed":
-            # k_tc_build_images32, k_tc_gram32, k_solve32, k_tc_grad32, k_reduce, k_adam
-            launches_per_step = 6
-            kernel_name = "k_tc_gram32 (tcgen05, 3 passes) + k_solve32 + k_tc_grad32 (tcgen05) + k_reduce + k_adam"
-        else:
-            n_sub = -(-nspec // max(1, min(nspec, (48 << 20) // (9 * grid.Npix + 4 * grid.Nb))))
-            launches_per_step = 2 * n_sub + 1 + 1
-            kernel_name = "k_gram_solve + k_grad (CUDA cores) + k_reduce + k_adam"
-    else:
-        want = ("nll", "hmean", "hcov", "cont", "unc") if kind == "predict" else ("nll",)
+    elif kind in ("predict", "score"):
         outs = {"nll": torch.empty(nspec, device=dev)}
         if kind == "predict":
             outs.update(hmean=torch.empty(nspec, Nh, device=dev), hcov=torch.empty(nspec, Nh, Nh, device=dev),
                         cont=torch.empty(nspec, grid.Npix, device=dev), unc=torch.empty(nspec, grid.Npix, device=dev))
-        if args.precision == "fp64":
+        if precision == "fp64":
             outs = {k: v.double() for k, v in outs.items()}
-
-        def step():
-            m.predict_into(X, E, Z, M, outs)
-        if Nh <= 8 and args.precision == "mixed":
-            launches_per_step = 2          # k_tc_build_images, k_tc_gram<PREDICT>
-            kernel_name = "k_tc_gram<PREDICT> (tcgen05 Gram GEMM + solve + continuum GEMM)"
+        if kind == "score":
+            def step():
+                m.predict_into(X, E, Z, M, outs)
+                res["ood"] = m.ood_select(outs["nll"].float(), threshold=None, k=256)     # on-device top-k of the NLLs
         else:
-            launches_per_step = 1
-            kernel_name = "k_gram_solve (CUDA cores)"
+            def step():
+                m.predict_into(X, E, Z, M, outs)
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
-    ms, t0, t1 = timed(step, args.steps, args.warmup, world)
+    n0 = L.qfa_launch_count()
+    ms, t0, t1 = timed(step, steps, args.warmup, world)
+    n1 = L.qfa_launch_count()
     clocks = sampler.stop(t0, t1) if sampler else None
-    if kind == "train":
+    if kind == "graph_train":
+        launches = launches_per_step * steps
+        launch_note = "kernel nodes of the captured step graph (counted by the library at capture) x replays"
+    else:
+        launches = int((n1 - n0) * steps // (steps + args.warmup))
+        launch_note = "counted by the library (qfa_launch_count) over the timed steps"
+    if kind in ("train", "graph_train"):
         m._params.copy_(p0)
-    value = world * nspec * args.steps / (ms * 1e-3)
+    value = world * nspec * steps / (ms * 1e-3)
     bps = bytes_per_spectrum("predict" if kind == "predict" else "train", grid.Npix, grid.Nb, Nh)
-    achieved = nspec * args.steps * bps / (ms * 1e-3) / 1e9        # per GPU, GB/s of algorithmic bytes
+    achieved = nspec * steps * bps / (ms * 1e-3) / 1e9        # per GPU, GB/s of algorithmic bytes
+    traffic, tsrc = committed_traffic(kind, grid_name, Nh, nspec)
     roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": measured_traffic(kind, grid_name, Nh, nspec),
-            "kernel": kernel_name, "bytes_per_spectrum": bps, "peak_source": peaks["source"]}
+            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": tsrc,
+            "kernel": kernel_names(kind, Nh, precision), "bytes_per_spectrum": bps, "peak_source": peaks["source"]}
     if Nh > 8 and kind == "train":
         # Nh = 32 is tensor-bound (SURVEY.md section 8d: AI ~ 330 FLOP/B): algorithmic FLOPs per spectrum
         # n*[H(H+1)(2+r_b) + 2H^2 + 8H + 30] + 3H^3 against the TF32 tensor peak (= half the measured bf16 peak)
         n_un = float(M.float().sum() / nspec)
         r_b = float(M[:, :grid.Nb].float().sum() / max(1.0, float(M.float().sum())))
         flops = n_un * (Nh * (Nh + 1) * (2 + r_b) + 2 * Nh * Nh + 8 * Nh + 30) + 3 * Nh ** 3
-        tf = nspec * args.steps * flops / (ms * 1e-3) / 1e12
+        tf = nspec * steps * flops / (ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": tf, "peak": peaks["tf32_tflops"], "unit": "TFLOP/s",
-                "frac": tf / peaks["tf32_tflops"], "traffic": None, "kernel": kernel_name,
-                "flops_per_spectrum": flops, "peak_source": peaks["tf32_source"]}
-    res.update(value=value, ms_per_step=ms / args.steps, clocks=clocks, gpu_launches=launches_per_step * args.steps,
-               roofline=roof,
-               config={"workload": name, "kind": kind, "grid": grid_name, "Npix": grid.Npix, "Nb": grid.Nb, "Nh": Nh,
-                       "spectra_per_gpu_per_step": nspec, "precision": args.precision,
-                       "l2": "inputs per step exceed L2 (%.0f MB)" % (nspec * (9 * grid.Npix + 4 * grid.Nb) / 1e6)})
+                "frac": tf / peaks["tf32_tflops"], "traffic": traffic, "traffic_source": tsrc,
+                "kernel": kernel_names(kind, Nh, precision), "flops_per_spectrum": flops, "peak_source": peaks["tf32_source"]}
+    res.update(value=value, ms_per_step=ms / steps, clocks=clocks, gpu_launches=launches, gpu_launches_how=launch_note,
+               roofline=roof, config=workload_config(name, nspec, args.precision, world),
+               dtype={"fp64": "f64", "fp32": "f32"}.get(precision, "tf32"))
+    if "ood" in res:
+        res["ood"] = {"top_k": 256, "top_nll_max": float(res["ood"]["top_val"][0]), "top_nll_min": float(res["ood"]["top_val"][-1])}
     if want_e2e:
-        hX, hE, hZ, hM = (t.cpu().pin_memory() for t in (X, E, Z, M))
-        if kind == "train":
+        esteps = max(2, steps // 2)
+        if kind == "graph_train":
+            # end to end at the reference's batch size: host batch -> H2D -> forward -> all-reduce -> update -> loss D2H
+            hb = synth.make_spectra(P, mu, grid, nspec, seed=99 + rank, **kw)
+            hX, hE, hZ, hM = (hb[k].pin_memory() for k in ("delta", "error", "zabs", "mask"))
+            opt2 = Adam(params=m.parameters, device=dev, scheduler=step_scheduler(0.9, 10), learning_rate=1e-3, weight_decay=0.1)
+            hl = torch.empty(1, dtype=torch.float64).pin_memory()
+
+            def estep():
+                dX, dE, dZ, dM = (t.to(dev, non_blocking=True) for t in (hX, hE, hZ, hM))
+                acc = m.accumulate(dX, dE, dZ, dM, zero=True)
+                m._allreduce(acc)
+                opt2.update_from_acc(m, acc)
+                hl.copy_(m._loss_from_acc(acc).view(1), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            h2d = sum(t.numel() * t.element_size() for t in (hX, hE, hZ, hM))
+            d2h = 8
+        elif kind == "train":
+            hX, hE, hZ, hM = (t.cpu().pin_memory() for t in (X, E, Z, M))
+
             def estep():
                 m.forward_host(hX, hE, hZ, hM)
             h2d = sum(t.numel() * t.element_size() for t in (hX, hE, hZ, hM))
             d2h = (m.Nparams + 1) * 4
         else:
+            hX, hE, hZ, hM = (t.cpu().pin_memory() for t in (X, E, Z, M))
             hout = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outs.items()}
 
             def estep():
                 m.predict_host(hX, hE, hZ, hM, out=hout, want=tuple(outs))
             h2d = sum(t.numel() * t.element_size() for t in (hX, hE, hZ, hM))
             d2h = sum(t.numel() * t.element_size() for t in hout.values())
-        ems, _, _ = timed(estep, max(2, args.steps // 2), 1, world)
-        res["e2e"] = {"value": world * nspec * max(2, args.steps // 2) / (ems * 1e-3), "unit": "spectra/s",
-                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+        ems, _, _ = timed(estep, esteps, 1, world)
+        if kind in ("train", "graph_train"):
+            m._params.copy_(p0)
+        res["e2e"] = {"value": world * nspec * esteps / (ems * 1e-3), "unit": "spectra/s",
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": esteps}
         del hX, hE, hZ, hM
     if want_cpu and rank == 0:
-        v, cms, cores, desc = cpu_reference_run(name, 1, 1, sample)
-        res["cpu_baseline"] = {"value": v, "unit": "spectra/s", "cores": cores, "kind": "port", "sample": desc}
-    del d, X, E, Z, M
+        res["cpu_baseline"], _ = cpu_run(name, 1, 1)
     torch.cuda.empty_cache()
     return res
+
+
+def dp_parity_check(rank, world):
+    """Inside the N > 1 run: the all-reduced accumulation buffer is bit-identical on every rank, and equals the buffer a
+    single rank computes over the SAME global batch (counts exactly, sums to float round-off of the summation order)."""
+    import torch.distributed as dist
+    from qfa_b200 import QFA, synth
+    grid, P, mu = model_and_params("sdss", 8)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    m = QFA(grid.Nb, grid.Nr, 8, dev, model_params={k: v.numpy() for k, v in P.items()}, precision="tf32")
+    m.enable_data_parallel()
+    B = 1536
+    d = synth.make_spectra(P, mu, grid, B, seed=777 + rank, device=dev)
+    ins = [d["delta"], d["error"], d["zabs"], d["mask"].view(torch.uint8)]
+    acc = m.accumulate(*ins, zero=True).clone()
+    dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    gathered = [torch.empty_like(acc) for _ in range(world)]
+    dist.all_gather(gathered, acc)
+    identical = all(torch.equal(g.view(torch.int32), gathered[0].view(torch.int32)) for g in gathered)
+    full = []
+    for t in ins:
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t.contiguous())
+        full.append(torch.cat(parts))
+    single = QFA(grid.Nb, grid.Nr, 8, dev, model_params={k: v.numpy() for k, v in P.items()}, precision="tf32")
+    acc1 = single.accumulate(*full, zero=True)
+    n = m.Nparams
+    cnt_equal = bool(torch.equal(acc[n:n + grid.Npix + 3], acc1[n:n + grid.Npix + 3])) and float(acc[n + grid.Npix + 4]) == B * world
+    rel = float((acc[:n] - acc1[:n]).abs().max() / acc1[:n].abs().max())
+    rel_nll = abs(float(acc[n + grid.Npix + 3]) - float(acc1[n + grid.Npix + 3])) / abs(float(acc1[n + grid.Npix + 3]))
+    ok = identical and cnt_equal and rel < 1e-4 and rel_nll < 1e-5
+    return {"ok": bool(ok), "bit_identical_across_ranks": bool(identical), "counts_equal_single_rank": cnt_equal,
+            "grad_sums_vs_single_rank_max_rel": rel, "nll_sum_vs_single_rank_rel": rel_nll,
+            "global_batch": B * world, "note": "dp_parity: ok" if ok else "dp_parity: FAILED"}
 
 
 def main():
@@ -368,6 +557,7 @@ def main():
         sys.exit(1)
     rank, world, local = dist_setup(args.gpus)
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local)
     if local == 0:
         from qfa_b200 import _lib
         _lib.build()                      # no-op when libqfa_b200.so is up to date
@@ -382,16 +572,24 @@ def main():
         peaks = {"hbm_gbs": float(mp["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)",
                  "tf32_tflops": float(mp.get("bf16_tflops_sustained", mp.get("bf16_tflops", 1590.0))) / 2,
                  "tf32_source": "half of the measured sustained bf16 peak (MEASURED_PEAKS.json)"}
-    main_res = measure_workload(args.workload, args, rank, world, peaks, not args.no_e2e, not args.no_cpu_baseline,
-                                args.spectra)
+    head = headline_for(world, args.workload)
+    dp = dp_parity_check(rank, world) if world > 1 else None
+    if dp is not None and not dp["ok"]:
+        if rank == 0:
+            emit({"error": "data-parallel parity check failed", "dp_parity": dp})
+        sys.exit(2)
+    main_res = measure_workload(head, args, rank, world, peaks, not args.no_e2e, not args.no_cpu_baseline, args.spectra)
     also = {}
-    if not args.no_also:
-        for name in ("sdss_train", "l32_train"):
-            if name == args.workload:
-                continue
-            r = measure_workload(name, args, rank, world, peaks, False, False)
-            also[name] = {"value": r["value"], "unit": "spectra/s", "ms_per_step": r["ms_per_step"],
-                          "roofline": r["roofline"], "config": r["config"], "gpu_launches": r["gpu_launches"]}
+    names = []
+    if not args.no_also and args.also != "none":
+        names = DEFAULT_ALSO[1 if world == 1 else 0] if args.also == "default" else [s for s in args.also.split(",") if s]
+    for name in names:
+        if name == head:
+            continue
+        r = measure_workload(name, args, rank, world, peaks, not args.no_e2e, not args.no_cpu_baseline and world == 1)
+        also[name] = {k: r[k] for k in ("value", "ms_per_step", "roofline", "config", "gpu_launches", "gpu_launches_how",
+                                         "clocks", "dtype", "e2e", "cpu_baseline", "ood") if k in r}
+        also[name]["unit"] = "spectra/s"
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -399,13 +597,16 @@ def main():
         line = {"metric": "spectra/sec", "value": main_res["value"], "unit": "spectra/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
+                "dtype": main_res["dtype"], "data": "synthetic",
                 "config": main_res["config"], "clocks": main_res["clocks"], "gpu_launches": main_res["gpu_launches"],
-                "roofline": main_res["roofline"]}
-        if "e2e" in main_res:
-            line["e2e"] = main_res["e2e"]
-        if "cpu_baseline" in main_res:
-            line["cpu_baseline"] = main_res["cpu_baseline"]
+                "gpu_launches_how": main_res["gpu_launches_how"], "roofline": main_res["roofline"], "numa": numa}
+        if world > 1:
+            line["scaling_note"] = ("headline at N > 1 is the data-parallel train step (one NCCL all-reduce per step); its N = 1 "
+                                    "value is also.sdss_train.value of the N = 1 line, NOT that line's predict headline")
+            line["dp_parity"] = dp
+        for k in ("e2e", "cpu_baseline"):
+            if k in main_res:
+                line[k] = main_res[k]
         if also:
             line["also"] = also
         emit(line)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define QFA_ABI_VERSION 1
+#define QFA_ABI_VERSION 2
 
 /* precision modes */
 #define QFA_PREC_FP64 0 /* double everywhere; parity mode (<=1e-5 vs fp64-promoted reference) */
@@ -53,6 +53,10 @@ extern "C" {
                                    8 < Nh <= 32: 192 spectra; env QFA_TC_MIN_BATCH overrides) */
 #define QFA_FLAG_SOLVE_FP64 4   /* QFA_PREC_TF32, 8 < Nh <= 32: per-spectrum Cholesky in double instead of float (7 % slower
                                    train step; no measurable difference on any parity case, kept for ill-conditioned models) */
+
+#define QFA_FLAG_TF32X3 8       /* QFA_PREC_TF32 tensor-core kernels: 3xTF32 operand splitting (hi/lo parts of both operands,
+                                   three MMAs per product, fp32 accumulation): operand rounding error ~2^-21 instead of
+                                   2^-11, i.e. float-level results from the tensor cores at ~1/3 of the tensor rate */
 
 /* error codes (negative) */
 #define QFA_ERR_NULL -1
@@ -160,10 +164,10 @@ int qfa_clip(float* params, int Nb, int Nr, int Nh, float min_value, float max_v
 int qfa_smooth(const float* params_in, float* params_out, int Nb, int Nr, int Nh, void* stream);
 
 /*
- * Device-side data preparation (reference QFA/dataloader.py:102,135-136, Ly-alpha
- * only -- exact on grids that start redward of Ly-beta such as the SDSS one):
- *   zabs[b,i]  = (1+zqso[b]) * wav[i] / 1215.67 - 1            (i < Nb)
- *   delta[b,i] = flux[b,i] - mu[i] * exp(-tau(zabs[b,i]))      (A = 1 for i >= Nb)
+ * Device-side data preparation (reference QFA/dataloader.py:102,135-136 with the multi-series
+ * optical depth tau_total of utils.py:174-203):
+ *   zabs[b,i]  = (1+zqso[b]) * wav[i] / 1215.67 - 1                  (i < Nb)
+ *   delta[b,i] = flux[b,i] - mu[i] * exp(-tau_total(zqso[b], wav[i])) (A = 1 for i >= Nb)
  * wav: float[Npix] rest-frame grid; either output may be NULL.
  */
 int qfa_prepare_batch(const float* flux, const float* zqso, const float* wav, const float* mu,
@@ -171,39 +175,66 @@ int qfa_prepare_batch(const float* flux, const float* zqso, const float* wav, co
                       float* zabs_out, float* delta_out, void* stream);
 
 /*
- * Hardware self-test of the tcgen05 / TMEM / bulk-copy plumbing used by the QFA_PREC_TF32 kernels:
- * D[128][64] = [ A[128][32] * B[48][32]^T | A * B[32:48]^T ] with B given as the swizzled
- * shared-memory image (hi and lo parts).  split != 0 selects the 3xTF32 product.
- * err_flag (device int) is set to 1 if an mbarrier wait timed out.  Test-only entry point.
+ * ---- rows "next" of SURVEY.md section 8f: the callers and data formats either side of the hot path ----
  */
-int qfa_selftest_umma(const float* A, const float* Bimg_hi, const float* Bimg_lo, float* D, int split,
-                      int* err_flag, void* stream);
 
 /*
- * Self-test of a 2-D TMA tile load (cp.async.bulk.tensor.2d through a tensor map encoded at run time) from a pitched
- * row-major float array src[rows][pitch_px] with npix valid pixels per row: out[120][32] = the box starting at row y0,
- * pixel x0 (out-of-range elements = 0).  pitch_px * 4 must be a multiple of 16 (QFA_ERR_ALIGN otherwise: this is exactly
- * why the dense reference layout with odd Npix cannot use TMA).  Test-only entry point.
+ * Same as qfa_adam_clip_step with the gradient read from `acc`, but the EPOCH-dependent scalars come from DEVICE
+ * memory: hyper_dev = {lr_i, 1 - b1^(i+1), 1 - b2^(i+1)} (optimizer.py:50-52,98).  A CUDA graph that captured the
+ * train step (gather/prepare -> accumulate -> all-reduce -> update) therefore stays valid across epochs.
+ * Optional, all device pointers: loss_sum_dev[0] += (sum NLL / #spectra) * loss_scale  (model.py:213 with
+ * loss_scale = 1 / Niter); cursor_dev[0] += cursor_step (the batch cursor of qfa_gather_prepare).
  */
-int qfa_selftest_tma2d(const float* src, int rows, int npix, int pitch_px, int x0, int y0, float* out, int* err_flag,
-                       void* stream);
-
-/* Streaming micro-benchmark of the same TMA tile path: one persistent kernel reads src[rows][pitch_px] once through 4-stage
- * rings of 120 x box_w boxes (box_w = 32, 64 or 128).  The caller times it.  Test / design aid. */
-int qfa_bench_tma2d(const float* src, int rows, int npix, int pitch_px, int box_w, float* sink, int* err_flag, void* stream);
-
-/* ... and through the per-thread loader pattern of the production kernels (15 warps x 8 rows, 128-byte row segments, two
- * register buffers), any pitch.  Test / design aid. */
-int qfa_bench_ldg(const float* src, int rows, int npix, int pitch_px, float* sink, void* stream);
+int qfa_adam_clip_step_dev(float* params, float* m, float* v, const void* acc,
+                           int Nb, int Nr, int Nh, int precision, const float* hyper_dev,
+                           float b1, float b2, float eps, float weight_decay,
+                           float min_value, float max_value,
+                           double* loss_sum_dev, double loss_scale,
+                           long long* cursor_dev, long long cursor_step, void* stream);
 
 /*
- * Debug/profiling aid: `device_buffer` (long long[nkb * 16 * 4], or NULL to switch off) receives clock64 stamps of
- * the first tile of CTA 0 of every following k_tc_gram launch: per K-block and warp {enter, stage free, operands
- * written, done}.  Not part of the reference-facing surface.
+ * qfa_prepare_batch for a SHUFFLED batch of a device-resident data set (reference QFA/dataloader.py:124-138 after
+ * rewind(), dataloader.py:154-167): batch row b is data-set row perm[cursor + b] (perm == NULL: row cursor + b;
+ * cursor_dev == NULL: 0; both are int64 DEVICE memory so that a captured graph needs no host argument).
+ * Writes the four tensors QFA.forward takes: delta (B,Npix), error (B,Npix), zabs (B,Nb), mask (B,Npix bytes);
+ * any output may be NULL.  delta uses the TOTAL Lyman-series optical depth (utils.py:174-203, all 30 lines of
+ * QFA/Lyman_series.csv; on grids redward of Ly-beta this is Ly-alpha only).
  */
-int qfa_debug_set_trace(void* device_buffer);
-/* same for k_tc_grad: CTA (0,0), long long[nchunks_of_that_cta * 16 * 8]: per chunk and warp 8 stamps */
-int qfa_debug_set_trace_grad(void* device_buffer);
+int qfa_gather_prepare(const float* flux, const float* error, const uint8_t* mask, const float* zqso,
+                       const float* wav, const float* mu, const long long* perm, const long long* cursor_dev,
+                       int B, int Nb, int Nr, int tau_law,
+                       float* zabs_out, float* delta_out, float* error_out, uint8_t* mask_out, void* stream);
+
+/*
+ * Column sums of the mean spectrum (dataloader.py:110-111), N spectra resident on the device:
+ *   sums[i]        = sum_b flux[b,i] * exp(+tau_total(b,i)) * mask[b,i]      (tau = 0 for i >= Nb)
+ *   sums[Npix + i] = #{ b : flux[b,i] != -999 }
+ * double[2*Npix]; all-reduce them across ranks, divide, then smooth on the host (utils.py:206-219).
+ */
+int qfa_mean_spectrum_sums(const float* flux, const uint8_t* mask, const float* zqso, const float* wav,
+                           int N, int Nb, int Nr, int tau_law, double* sums, void* stream);
+
+/*
+ * Out-of-distribution scoring on per-spectrum NLLs (the consumer of qfa_predict's nll-only mode; BASELINE config 3):
+ *   count_out[0] = #{ b : nll[b] > threshold } (NaN counts), the first min(count, thr_cap) hits go to thr_idx
+ *   (unordered);  top_idx/top_val[0..k) = the k largest NLLs, descending, ties by ascending index (k <= 2048).
+ * count_out == NULL skips the threshold pass; k == 0 skips the top-k.  All pointers are device memory.
+ */
+int qfa_ood_select(const float* nll, int B, float threshold, int k, int thr_cap,
+                   int* count_out, int* thr_idx, int* top_idx, float* top_val, void* stream);
+
+/*
+ * Posterior samples of the latent vector and of the continuum (nb/predict.ipynb cell 11:
+ * np.random.multivariate_normal(hmean, hcov); mu + F @ hsample):  h = hmean + chol(hcov) z, z ~ N(0, I) from
+ * Philox4x32-10 keyed by (seed, spectrum, sample, component) -- reproducible for a given seed.
+ * hmean (B,Nh), hcov (B,Nh,Nh) float as qfa_predict returns them.  Outputs (any may be NULL):
+ * z_out, h_out (B,S,Nh); cont_out (B,S,Npix).
+ */
+int qfa_sample_posterior(const QfaModel* model, const float* hmean, const float* hcov, int B, int S,
+                         unsigned long long seed, float* z_out, float* h_out, float* cont_out, void* stream);
+
+/* Number of kernel launches this library has issued in this process (what bench.py reports as gpu_launches). */
+unsigned long long qfa_launch_count(void);
 
 #ifdef __cplusplus
 }

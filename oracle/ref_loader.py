@@ -24,8 +24,41 @@ def reference_available() -> bool:
     return os.path.isfile(os.path.join(REF_ROOT, "QFA", "model.py"))
 
 
-def load_reference(fp64: bool = False):
+def find_reference():
+    """Root of an importable copy of the UNMODIFIED reference: $QFA_REF, baseline/_ref (the pip --target install that
+    travels to the GPU box), or /root/reference (build container only).  None if there is none."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for root in (os.environ.get("QFA_REF"), os.path.join(here, "baseline", "_ref"), "/root/reference"):
+        if root and os.path.isfile(os.path.join(root, "QFA", "model.py")):
+            return root
+    return None
+
+
+def _csv_dir(root):
+    """Directory to chdir into for the import.  The reference reads './Lyman_series.csv' from the CWD (utils.py:144); its
+    setup.py does not ship the file (package_data lists only README/LICENSE), so for a pip-installed copy the same table
+    (atomic data, qfa_b200.utils._LYMAN) is written to a scratch directory in the reference's column layout."""
+    d = os.path.join(root, "QFA")
+    if os.path.isfile(os.path.join(d, "Lyman_series.csv")):
+        return d
+    import tempfile
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    from qfa_b200.utils import _LYMAN
+    tmp = tempfile.mkdtemp(prefix="qfa_ref_cwd_")
+    with open(os.path.join(tmp, "Lyman_series.csv"), "w") as fh:
+        fh.write("name,f,lambda,coeff\n")
+        for f, lam in _LYMAN:
+            fh.write(f"HI_{int(lam)},{f:.4e},{lam:.4f},-1\n")
+    return tmp
+
+
+def load_reference(fp64: bool = False, root: str = None):
     """Returns (QFA_class, Adam_class, step_scheduler, utils_module)."""
+    global REF_ROOT
+    if root is not None:
+        REF_ROOT = root
     if not reference_available():
         raise RuntimeError(f"reference not found under {REF_ROOT}")
     if "yacs" not in sys.modules:
@@ -53,7 +86,7 @@ def load_reference(fp64: bool = False):
         torch.float = torch.float64
         torch.set_default_dtype(torch.float64)
     cwd = os.getcwd()
-    os.chdir(os.path.join(REF_ROOT, "QFA"))
+    os.chdir(_csv_dir(REF_ROOT))
     try:
         if REF_ROOT not in sys.path:
             sys.path.insert(0, REF_ROOT)

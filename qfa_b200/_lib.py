@@ -12,8 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libqfa_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "qfa_capi.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", "qfa_common.cuh"), os.path.join(_HERE, "csrc", "qfa_kernels.cuh"),
-           os.path.join(_ROOT, "include", "qfa_b200.h")]
+HEADERS = [os.path.join(_ROOT, "include", "qfa_b200.h"), os.path.join(_ROOT, "include", "qfa_b200_debug.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -21,11 +20,13 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 PREC_FP64, PREC_FP32, PREC_TF32 = 0, 1, 2
 # "mixed": tensor cores above the path's cross-over batch size (predict 1280, train 512 / 192; env QFA_TC_MIN_BATCH),
 # float CUDA cores below; "tf32": always tensor cores
-PRECISIONS = {"fp64": PREC_FP64, "fp32": PREC_FP32, "mixed": PREC_TF32, "tf32": PREC_TF32}
+PRECISIONS = {"fp64": PREC_FP64, "fp32": PREC_FP32, "mixed": PREC_TF32, "tf32": PREC_TF32, "tf32x3": PREC_TF32}
 TAU_LAWS = {"becker": 0, "fg": 1, "kamble": 2, "mock": 3}
 FLAG_ZERO_ACC = 1
 FLAG_FORCE_TENSOR = 2
 FLAG_SOLVE_FP64 = 4
+FLAG_TF32X3 = 8
+ABI_VERSION = 2
 
 
 class QfaError(RuntimeError):
@@ -65,6 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 _lib = None
 
 _VP, _I, _F, _SZ = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+_D, _LL, _ULL = ctypes.c_double, ctypes.c_longlong, ctypes.c_ulonglong
 _MP = ctypes.POINTER(QfaModelStruct)
 
 # name -> (restype, argtypes); must list every symbol include/qfa_b200.h declares
@@ -79,9 +81,19 @@ SIGNATURES = {
     "qfa_grads_finalize": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP]),
     "qfa_predict": (_I, [_MP, _VP, _VP, _VP, _VP, _I, _VP, _SZ, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP]),
     "qfa_adam_clip_step": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _F, _F, _F, _F, _F, _F, _F, _F, _F, _VP]),
+    "qfa_adam_clip_step_dev": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP, _F, _F, _F, _F, _F, _F, _VP, _D, _VP, _LL,
+                                    _VP]),
     "qfa_clip": (_I, [_VP, _I, _I, _I, _F, _F, _VP]),
     "qfa_smooth": (_I, [_VP, _VP, _I, _I, _I, _VP]),
     "qfa_prepare_batch": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP]),
+    "qfa_gather_prepare": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "qfa_mean_spectrum_sums": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP, _VP]),
+    "qfa_ood_select": (_I, [_VP, _I, _F, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "qfa_sample_posterior": (_I, [_MP, _VP, _VP, _I, _I, _ULL, _VP, _VP, _VP, _VP]),
+    "qfa_launch_count": (_ULL, []),
+}
+# include/qfa_b200_debug.h: hardware self-tests, design micro-benchmarks, trace hooks (not reference-facing)
+DEBUG_SIGNATURES = {
     "qfa_selftest_umma": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP]),
     "qfa_selftest_tma2d": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP, _VP]),
     "qfa_bench_tma2d": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP]),
@@ -99,7 +111,7 @@ def lib():
             raise QfaError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(no CPU fallback exists)")
         L = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
+        for name, (res, args) in list(SIGNATURES.items()) + list(DEBUG_SIGNATURES.items()):
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args

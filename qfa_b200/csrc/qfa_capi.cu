@@ -7,6 +7,8 @@
 #include <string.h>
 
 #include "../../include/qfa_b200.h"
+#include "../../include/qfa_b200_debug.h"
+#include "qfa_aux.cuh"
 #include "qfa_kernels.cuh"
 #include "qfa_tc_selftest.cuh"
 #include "qfa_tc_gram.cuh"
@@ -39,12 +41,26 @@ static int cuda_fail(cudaError_t e, const char* what) {
 
 extern "C" int qfa_abi_version(void) { return QFA_ABI_VERSION; }
 
-// debug: device buffer that k_tc_gram fills with clock64 stamps of CTA 0's first tile (see TcGramArgs::trace)
+extern "C" const char* qfa_last_error_string(void) { return g_err; }
+
+// Kernel launches issued by this library in this process (bench.py's gpu_launches is this counter, not a constant).
+static unsigned long long g_launches = 0;
+#define QFA_LAUNCHED() (++g_launches)
+extern "C" unsigned long long qfa_launch_count(void) { return g_launches; }
+
+// debug (qfa_b200_debug.h): clock64 trace buffers of k_tc_gram / k_tc_grad.  Only a -DQFA_ENABLE_TRACE build keeps these
+// pointers; the production library keeps no pointer between calls and the setters report QFA_ERR_UNSUPPORTED.
+#ifdef QFA_ENABLE_TRACE
 static long long* g_trace = nullptr;
 static long long* g_trace_grad = nullptr;
 extern "C" int qfa_debug_set_trace(void* device_buffer) { g_trace = (long long*)device_buffer; return 0; }
 extern "C" int qfa_debug_set_trace_grad(void* device_buffer) { g_trace_grad = (long long*)device_buffer; return 0; }
-extern "C" const char* qfa_last_error_string(void) { return g_err; }
+#else
+static constexpr long long* g_trace = nullptr;
+static constexpr long long* g_trace_grad = nullptr;
+extern "C" int qfa_debug_set_trace(void*) { return fail(QFA_ERR_UNSUPPORTED, "built without -DQFA_ENABLE_TRACE"); }
+extern "C" int qfa_debug_set_trace_grad(void*) { return fail(QFA_ERR_UNSUPPORTED, "built without -DQFA_ENABLE_TRACE"); }
+#endif
 
 // ---------------------------------------------------------------------------------------
 // layouts
@@ -61,16 +77,28 @@ static inline int pad_h(int Nh) { return Nh <= 4 ? 4 : Nh <= 8 ? 8 : Nh <= 16 ? 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline size_t tsize(int precision) { return precision == QFA_PREC_FP64 ? 8 : 4; }
 
-static int g_num_sms = 0;
-static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-    }
-    return g_num_sms;
+// Per-DEVICE state: the SM count and the "dynamic shared memory opt-in done" flags belong to the device that is current
+// when an entry point runs (cudaFuncSetAttribute applies to the current device only), so they are keyed by its ordinal.
+constexpr int kMaxDevices = 64;
+static int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < kMaxDevices ? dev : 0;
 }
+static int num_sms() {
+    static int sms[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (sms[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
+    }
+    return sms[dev];
+}
+// one flag per (call site, device)
+struct PerDeviceOnce {
+    bool done[kMaxDevices] = {false};
+};
 
 // Spectra per sub-batch: sized so that one sub-batch of inputs stays L2-resident between the
 // spectrum-major pass and the pixel-major pass (B200: 126 MB L2).
@@ -317,11 +345,11 @@ template <typename T, int HP, int MODE>
 static cudaError_t launch_gram(const GramArgs<T>& a, cudaStream_t st) {
     using C = GramCfg<T, HP, MODE>;
     auto kern = k_gram_solve<T, HP, MODE>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (!attr_once.done[current_device()]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_once.done[current_device()] = true;
     }
     int per_sm = (int)((size_t)220 * 1024 / (C::smem_bytes + 1024));
     if (per_sm < 1) per_sm = 1;
@@ -329,7 +357,7 @@ static cudaError_t launch_gram(const GramArgs<T>& a, cudaStream_t st) {
     int grid = num_sms() * per_sm;
     if (grid > a.B) grid = a.B;
     if (grid < 1) return cudaSuccess;
-    kern<<<grid, C::NT, C::smem_bytes, st>>>(a);
+    kern<<<grid, C::NT, C::smem_bytes, st>>>(a); QFA_LAUNCHED();
     return cudaGetLastError();
 }
 
@@ -347,10 +375,10 @@ template <typename T>
 static cudaError_t dispatch_grad(int HP, const GradArgs<T>& a, int ntiles, cudaStream_t st) {
     dim3 grid(ntiles, a.nsplit);
     switch (HP) {
-        case 4: k_grad<T, 4><<<grid, 128, 0, st>>>(a); break;
-        case 8: k_grad<T, 8><<<grid, 128, 0, st>>>(a); break;
-        case 16: k_grad<T, 16><<<grid, 128, 0, st>>>(a); break;
-        default: k_grad<T, 32><<<grid, 128, 0, st>>>(a); break;
+        case 4: k_grad<T, 4><<<grid, 128, 0, st>>>(a); QFA_LAUNCHED(); break;
+        case 8: k_grad<T, 8><<<grid, 128, 0, st>>>(a); QFA_LAUNCHED(); break;
+        case 16: k_grad<T, 16><<<grid, 128, 0, st>>>(a); QFA_LAUNCHED(); break;
+        default: k_grad<T, 32><<<grid, 128, 0, st>>>(a); QFA_LAUNCHED(); break;
     }
     return cudaGetLastError();
 }
@@ -387,7 +415,7 @@ static int train_accumulate_t(const QfaModel* m, const float* delta, const float
     ra.ntiles_blue = pl.ntiles_blue; ra.ntiles = pl.ntiles; ra.nsplit_red = nsplit_used; ra.tile_px = 128;
     size_t n_el = part_len(P, Nb, Nh);
     int blocks = (int)((n_el + 255) / 256);
-    k_reduce<T><<<blocks, 256, 0, st>>>(ra);
+    k_reduce<T><<<blocks, 256, 0, st>>>(ra); QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }
@@ -409,14 +437,14 @@ static int train_accumulate_tc(const QfaModel* m, const float* delta, const floa
     const size_t n_el = (size_t)pl.t.nkb * PB_ROWS * KB + (size_t)pl.t.npt * 2 * PT * KB;
     int blocks = (int)((n_el + 255) / 256);
     if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
-    k_tc_build_images<<<blocks, 256, 0, st>>>(m->params, P, Nh, PB, pl.t.nkb, QA, pl.t.npt);
+    k_tc_build_images<<<blocks, 256, 0, st>>>(m->params, P, Nh, PB, pl.t.nkb, QA, pl.t.npt); QFA_LAUNCHED();
     CK(cudaGetLastError());
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (!attr_once.done[current_device()]) {
         CK(cudaFuncSetAttribute(k_tc_gram<TC_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<TC_TRAIN>::SMEM_BYTES));
         CK(cudaFuncSetAttribute(k_tc_grad<GCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GradSmem::BYTES));
         CK(cudaFuncSetAttribute(k_tc_grad<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GradSmem::BYTES));
-        attr_done = true;
+        attr_once.done[current_device()] = true;
     }
     Field<float> f = make_field<float>(m, delta, error, zabs, mask);
     TcGramArgs a;
@@ -424,7 +452,7 @@ static int train_accumulate_tc(const QfaModel* m, const float* delta, const floa
     a.PB = PB; a.QA = QA; a.nll = nll_out; a.hmean = nullptr; a.hcov = nullptr; a.cont = nullptr; a.unc = nullptr;
     a.sm_b2 = sm_b2; a.sm_kc = sm_kc; a.hasblue = nullptr; a.tile_sums = tsums; a.trace = g_trace;
     int grid = pl.t.ntiles < num_sms() ? pl.t.ntiles : num_sms();
-    k_tc_gram<TC_TRAIN><<<grid, NTHREADS, Cfg<TC_TRAIN>::SMEM_BYTES, st>>>(a);
+    k_tc_gram<TC_TRAIN><<<grid, NTHREADS, Cfg<TC_TRAIN>::SMEM_BYTES, st>>>(a); QFA_LAUNCHED();
     CK(cudaGetLastError());
     TcGradArgs ga;
     ga.f = f; ga.B = B; ga.ts = pl.t.ts; ga.nchunks = pl.nchunks; ga.gct = pl.gct; ga.ns_blue = pl.ns_blue; ga.ns_red = pl.ns_red;
@@ -434,13 +462,14 @@ static int train_accumulate_tc(const QfaModel* m, const float* delta, const floa
     const int grad_ctas = pl.ntiles_blue * pl.ns_blue + (pl.t.npt - pl.ntiles_blue) * pl.ns_red;
     if (pl.gct == GCT) k_tc_grad<GCT><<<grad_ctas, GRAD_THREADS, GradSmem::BYTES, st>>>(ga);
     else k_tc_grad<0><<<grad_ctas, GRAD_THREADS, GradSmem::BYTES, st>>>(ga);
+    QFA_LAUNCHED();
     CK(cudaGetLastError());
     ReduceArgs<float> ra;
     ra.part = part; ra.spart = spart; ra.nll = tsums; ra.hasblue = tsums + 1; ra.scal = f.scal;   // pre-folded per 32 rows
     ra.acc = acc; ra.P = P; ra.Nb = Nb; ra.Nh = Nh; ra.B = pl.t.ntiles * 4; ra.stride = 2; ra.nsp = (double)B;
     ra.nsplit = pl.ns_blue; ra.nsplit_red = pl.ns_red; ra.tile_px = PT; ra.ntiles_blue = pl.ntiles_blue; ra.ntiles = pl.t.npt;
     size_t n_pl = part_len(P, Nb, Nh);
-    k_reduce<float><<<(int)((n_pl + 255) / 256), 256, 0, st>>>(ra);
+    k_reduce<float><<<(int)((n_pl + 255) / 256), 256, 0, st>>>(ra); QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }
@@ -462,38 +491,39 @@ static int train_accumulate_tc32(const QfaModel* m, const float* delta, const fl
     const size_t n_el = (size_t)pl.nkb * PB32_ROWS * tcg::KB;
     int blocks = (int)((n_el + 255) / 256);
     if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-    k_tc_build_images32<<<blocks, 256, 0, st>>>(m->params, P, Nh, PB, pl.nkb);
+    k_tc_build_images32<<<blocks, 256, 0, st>>>(m->params, P, Nh, PB, pl.nkb); QFA_LAUNCHED();
     CK(cudaGetLastError());
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (!attr_once.done[current_device()]) {
         CK(cudaFuncSetAttribute(k_tc_gram32, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM32_BYTES));
         CK(cudaFuncSetAttribute(k_solve32<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE32_SMEM));
         CK(cudaFuncSetAttribute(k_solve32<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE32_SMEM));
         CK(cudaFuncSetAttribute(k_tc_grad32, cudaFuncAttributeMaxDynamicSharedMemorySize, G32_SMEM));
-        attr_done = true;
+        attr_once.done[current_device()] = true;
     }
     Field<float> f = make_field<float>(m, delta, error, zabs, mask);
     TcGram32Args a;
     a.f = f; a.B = B; a.ts = pl.ts; a.ntiles = pl.ntiles; a.nkb = pl.nkb; a.PB = PB; a.gram = gram; a.trace = g_trace;
     a.replay = reinterpret_cast<float*>(ws + pl.off_replay);
     int grid = pl.ntiles < num_sms() ? pl.ntiles : num_sms();
-    k_tc_gram32<<<grid, tcg::NTHREADS, SMEM32_BYTES, st>>>(a);
+    k_tc_gram32<<<grid, tcg::NTHREADS, SMEM32_BYTES, st>>>(a); QFA_LAUNCHED();
     CK(cudaGetLastError());
     int sblocks = (B + SOLVE32_WARPS - 1) / SOLVE32_WARPS;
     if (sblocks > QFA_SOLVE32_CTAS * num_sms()) sblocks = QFA_SOLVE32_CTAS * num_sms();
     if (flags & QFA_FLAG_SOLVE_FP64) k_solve32<double><<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, small, nll, hasblue);
     else k_solve32<float><<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, small, nll, hasblue);
+    QFA_LAUNCHED();
     CK(cudaGetLastError());
     TcGrad32Args gr;
     gr.f = f; gr.B = B; gr.nsplit = pl.nsplit; gr.img = small; gr.part = part; gr.spart = spart; gr.trace = g_trace_grad;
-    k_tc_grad32<<<dim3(pl.npix_tiles, pl.nsplit), G32_THREADS, G32_SMEM, st>>>(gr);
+    k_tc_grad32<<<dim3(pl.npix_tiles, pl.nsplit), G32_THREADS, G32_SMEM, st>>>(gr); QFA_LAUNCHED();
     CK(cudaGetLastError());
     ReduceArgs<float> ra;
     ra.part = part; ra.spart = spart; ra.nll = nll; ra.hasblue = hasblue; ra.scal = f.scal;
     ra.acc = acc; ra.P = P; ra.Nb = Nb; ra.Nh = Nh; ra.B = B; ra.stride = 1; ra.nsp = (double)B; ra.nsplit = pl.nsplit;
     ra.ntiles_blue = pl.ntiles_blue; ra.ntiles = pl.npix_tiles; ra.nsplit_red = pl.nsplit; ra.tile_px = 128;
     size_t n_pl = part_len(P, Nb, Nh);
-    k_reduce<float><<<(int)((n_pl + 255) / 256), 256, 0, st>>>(ra);
+    k_reduce<float><<<(int)((n_pl + 255) / 256), 256, 0, st>>>(ra); QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }
@@ -557,12 +587,12 @@ static int predict_tc(const QfaModel* m, const float* flux, const float* error, 
     const size_t n_el = (size_t)pl.nkb * PB_ROWS * KB + (want_o ? (size_t)pl.npt * 2 * PT * KB : 0);
     int blocks = (int)((n_el + 255) / 256);
     if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
-    k_tc_build_images<<<blocks, 256, 0, st>>>(m->params, P, m->Nh, PB, pl.nkb, want_o ? QA : nullptr, want_o ? pl.npt : 0);
+    k_tc_build_images<<<blocks, 256, 0, st>>>(m->params, P, m->Nh, PB, pl.nkb, want_o ? QA : nullptr, want_o ? pl.npt : 0); QFA_LAUNCHED();
     CK(cudaGetLastError());
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (!attr_once.done[current_device()]) {
         CK(cudaFuncSetAttribute(k_tc_gram<TC_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_done = true;
+        attr_once.done[current_device()] = true;
     }
     TcGramArgs a;
     a.f = make_field<float>(m, flux, error, zabs, mask);
@@ -570,7 +600,7 @@ static int predict_tc(const QfaModel* m, const float* flux, const float* error, 
     a.PB = PB; a.QA = QA; a.nll = nll; a.hmean = hmean; a.hcov = hcov; a.cont = cont; a.unc = unc;
     a.sm_b2 = nullptr; a.sm_kc = nullptr; a.hasblue = nullptr; a.tile_sums = nullptr; a.trace = g_trace;
     int grid = pl.ntiles < num_sms() ? pl.ntiles : num_sms();
-    k_tc_gram<TC_PREDICT><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(a);
+    k_tc_gram<TC_PREDICT><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(a); QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }
@@ -644,12 +674,22 @@ __device__ __forceinline__ float clip_elem(float p, const PLayout& L, size_t e, 
     return fminf(fmaxf(p, 0.1f), 5.0f);                                       // beta (model.py:240)
 }
 
+// hyper (device, optional): {lr, bias1, bias2} -- overrides the by-value arguments, so that a captured CUDA graph of the step
+// keeps working when the EPOCH counter (and with it the learning rate and the bias corrections, optimizer.py:50-52,98)
+// changes.  Thread 0 also folds the step's mean NLL into loss_sum (model.py:213: total_loss += loss / Niter) and advances
+// the data cursor of k_gather_prepare: a replayed step needs no host-side argument at all.
 template <typename T>
 __global__ void k_adam(float* p, float* m, float* v, const T* acc, const float* gin, PLayout L, int Nh,
                        float lr, float b1, float b2, float eps, float wd, float bias1, float bias2,
-                       float lo, float hi) {
+                       float lo, float hi, const float* hyper, double* loss_sum, double loss_scale,
+                       long long* cursor, long long cursor_step) {
     size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) {
+        if (loss_sum && acc) loss_sum[0] += (double)acc[L.o_nll] / (double)acc[L.o_nsp] * loss_scale;
+        if (cursor) cursor[0] += cursor_step;
+    }
     if (e >= L.n) return;
+    if (hyper) { lr = hyper[0]; bias1 = hyper[1]; bias2 = hyper[2]; }
     float g = gin ? gin[e] : grad_from_acc(acc, L, e, Nh);
     float pe = p[e];
     g = g + wd * pe;                                  // optimizer.py:47
@@ -689,21 +729,6 @@ __global__ void k_smooth(const float* in, float* out, PLayout L, int Nh) {
     }
 }
 
-__global__ void k_prepare(const float* flux, const float* zq, const float* wav, const float* mu, size_t B, int Nb,
-                          int P, float lt0, float lbe, float lC, float lzn, float* zabs, float* delta) {
-    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= B * (size_t)P) return;
-    size_t b = gid / P; int i = (int)(gid % P);
-    float A = 1.0f;
-    if (i < Nb) {
-        float z = (1.0f + zq[b]) * wav[i] / 1215.67f - 1.0f;          // dataloader.py:102
-        if (zabs) zabs[b * (size_t)Nb + i] = z;
-        float tau = lt0 * powf((1.0f + z) / lzn, lbe) + lC;
-        A = expf(-tau);
-    }
-    if (delta) delta[gid] = flux[gid] - mu[i] * A;                    // dataloader.py:135-136
-}
-
 static int check_grid(int Nb, int Nr, int Nh) {
     if (Nb < 0 || Nr < 0 || Nb + Nr <= 0) return fail(QFA_ERR_SHAPE, "bad grid Nb=%d Nr=%d", Nb, Nr);
     if (Nh < 1 || Nh > 32) return fail(QFA_ERR_NH, "Nh=%d unsupported (1..32)", Nh);
@@ -720,14 +745,15 @@ extern "C" int qfa_grads_finalize(const void* acc, int Nb, int Nr, int Nh, int p
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == QFA_PREC_FP64) k_finalize<double><<<blocks, 256, 0, st>>>((const double*)acc, L, Nh, grads, loss);
     else k_finalize<float><<<blocks, 256, 0, st>>>((const float*)acc, L, Nh, grads, loss);
+    QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }
 
-extern "C" int qfa_adam_clip_step(float* params, float* m, float* v, const void* acc, const float* grads_in,
-                                  int Nb, int Nr, int Nh, int precision, float lr, float b1, float b2, float eps,
-                                  float weight_decay, float bias1, float bias2, float min_value, float max_value,
-                                  void* stream) {
+static int adam_launch(float* params, float* m, float* v, const void* acc, const float* grads_in, int Nb, int Nr, int Nh,
+                       int precision, float lr, float b1, float b2, float eps, float weight_decay, float bias1, float bias2,
+                       float min_value, float max_value, const float* hyper, double* loss_sum, double loss_scale,
+                       long long* cursor, long long cursor_step, void* stream) {
     int rc = check_grid(Nb, Nr, Nh);
     if (rc) return rc;
     if (!params || !m || !v || (!acc && !grads_in)) return fail(QFA_ERR_NULL, "params/m/v/acc is NULL");
@@ -736,12 +762,32 @@ extern "C" int qfa_adam_clip_step(float* params, float* m, float* v, const void*
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == QFA_PREC_FP64 && !grads_in)
         k_adam<double><<<blocks, 256, 0, st>>>(params, m, v, (const double*)acc, grads_in, L, Nh, lr, b1, b2, eps,
-                                               weight_decay, bias1, bias2, min_value, max_value);
+                                               weight_decay, bias1, bias2, min_value, max_value, hyper, loss_sum, loss_scale,
+                                               cursor, cursor_step);
     else
         k_adam<float><<<blocks, 256, 0, st>>>(params, m, v, (const float*)acc, grads_in, L, Nh, lr, b1, b2, eps,
-                                              weight_decay, bias1, bias2, min_value, max_value);
+                                              weight_decay, bias1, bias2, min_value, max_value, hyper, loss_sum, loss_scale,
+                                              cursor, cursor_step);
+    QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int qfa_adam_clip_step(float* params, float* m, float* v, const void* acc, const float* grads_in,
+                                  int Nb, int Nr, int Nh, int precision, float lr, float b1, float b2, float eps,
+                                  float weight_decay, float bias1, float bias2, float min_value, float max_value,
+                                  void* stream) {
+    return adam_launch(params, m, v, acc, grads_in, Nb, Nr, Nh, precision, lr, b1, b2, eps, weight_decay, bias1, bias2,
+                       min_value, max_value, nullptr, nullptr, 0.0, nullptr, 0, stream);
+}
+
+extern "C" int qfa_adam_clip_step_dev(float* params, float* m, float* v, const void* acc, int Nb, int Nr, int Nh,
+                                      int precision, const float* hyper_dev, float b1, float b2, float eps,
+                                      float weight_decay, float min_value, float max_value, double* loss_sum_dev,
+                                      double loss_scale, long long* cursor_dev, long long cursor_step, void* stream) {
+    if (!hyper_dev) return fail(QFA_ERR_NULL, "hyper_dev is NULL");
+    return adam_launch(params, m, v, acc, nullptr, Nb, Nr, Nh, precision, 0.f, b1, b2, eps, weight_decay, 1.f, 1.f,
+                       min_value, max_value, hyper_dev, loss_sum_dev, loss_scale, cursor_dev, cursor_step, stream);
 }
 
 extern "C" int qfa_clip(float* params, int Nb, int Nr, int Nh, float min_value, float max_value, void* stream) {
@@ -749,7 +795,7 @@ extern "C" int qfa_clip(float* params, int Nb, int Nr, int Nh, float min_value, 
     if (rc) return rc;
     if (!params) return fail(QFA_ERR_NULL, "params is NULL");
     PLayout L = playout(Nb, Nr, Nh);
-    k_clip<<<(int)((L.n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, L, min_value, max_value);
+    k_clip<<<(int)((L.n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, L, min_value, max_value); QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }
@@ -760,22 +806,93 @@ extern "C" int qfa_smooth(const float* params_in, float* params_out, int Nb, int
     if (!params_in || !params_out) return fail(QFA_ERR_NULL, "params is NULL");
     if (params_in == params_out) return fail(QFA_ERR_UNSUPPORTED, "qfa_smooth cannot run in place");
     PLayout L = playout(Nb, Nr, Nh);
-    k_smooth<<<(int)((L.n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params_in, params_out, L, Nh);
+    k_smooth<<<(int)((L.n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params_in, params_out, L, Nh); QFA_LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static aux::Law aux_law(int tau_law) {
+    LawConst lc = law_constants(tau_law);
+    aux::Law lw; lw.t0 = (float)lc.t0; lw.be = (float)lc.be; lw.C = (float)lc.C; lw.zn = (float)lc.zn;
+    return lw;
+}
+
+static int gather_prepare(const float* flux, const float* error, const uint8_t* mask, const float* zqso, const float* wav,
+                          const float* mu, const long long* perm, const long long* cursor, int B, int Nb, int Nr, int tau_law,
+                          float* zabs_out, float* delta_out, float* error_out, uint8_t* mask_out, void* stream) {
+    if (Nb < 0 || Nr < 0 || Nb + Nr <= 0 || B < 0) return fail(QFA_ERR_SHAPE, "bad shape");
+    if (tau_law < 0 || tau_law > 3) return fail(QFA_ERR_LAW, "unknown tau law %d", tau_law);
+    if (!zqso || !wav || (delta_out && (!flux || !mu)) || (error_out && !error) || (mask_out && !mask))
+        return fail(QFA_ERR_NULL, "NULL input");
+    if (B == 0) return 0;
+    aux::PrepArgs a;
+    a.flux = flux; a.error = error; a.mask = mask; a.zq = zqso; a.wav = wav; a.mu = mu;
+    a.perm = reinterpret_cast<const int64_t*>(perm); a.cursor = reinterpret_cast<const int64_t*>(cursor);
+    a.B = B; a.Nb = Nb; a.P = Nb + Nr; a.max_series = aux::kNSeries; a.lw = aux_law(tau_law);
+    a.zabs_out = zabs_out; a.delta_out = delta_out; a.error_out = error_out; a.mask_out = mask_out;
+    const int gx = (a.P + 255) / 256;
+    int gy = B < 65535 ? B : 65535;
+    aux::k_gather_prepare<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(a); QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }
 
 extern "C" int qfa_prepare_batch(const float* flux, const float* zqso, const float* wav, const float* mu, int B,
                                  int Nb, int Nr, int tau_law, float* zabs_out, float* delta_out, void* stream) {
-    if (Nb < 0 || Nr < 0 || Nb + Nr <= 0 || B < 0) return fail(QFA_ERR_SHAPE, "bad shape");
+    return gather_prepare(flux, nullptr, nullptr, zqso, wav, mu, nullptr, nullptr, B, Nb, Nr, tau_law, zabs_out, delta_out,
+                          nullptr, nullptr, stream);
+}
+
+extern "C" int qfa_gather_prepare(const float* flux, const float* error, const uint8_t* mask, const float* zqso,
+                                  const float* wav, const float* mu, const long long* perm, const long long* cursor_dev,
+                                  int B, int Nb, int Nr, int tau_law, float* zabs_out, float* delta_out, float* error_out,
+                                  uint8_t* mask_out, void* stream) {
+    return gather_prepare(flux, error, mask, zqso, wav, mu, perm, cursor_dev, B, Nb, Nr, tau_law, zabs_out, delta_out,
+                          error_out, mask_out, stream);
+}
+
+extern "C" int qfa_mean_spectrum_sums(const float* flux, const uint8_t* mask, const float* zqso, const float* wav, int N,
+                                      int Nb, int Nr, int tau_law, double* sums, void* stream) {
+    if (Nb < 0 || Nr < 0 || Nb + Nr <= 0 || N < 0) return fail(QFA_ERR_SHAPE, "bad shape");
     if (tau_law < 0 || tau_law > 3) return fail(QFA_ERR_LAW, "unknown tau law %d", tau_law);
-    if (!zqso || !wav || (delta_out && (!flux || !mu))) return fail(QFA_ERR_NULL, "NULL input");
-    if (B == 0) return 0;
-    LawConst lc = law_constants(tau_law);
-    size_t n = (size_t)B * (Nb + Nr);
-    k_prepare<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        flux, zqso, wav, mu, (size_t)B, Nb, Nb + Nr, (float)lc.t0, (float)lc.be, (float)lc.C, (float)lc.zn, zabs_out,
-        delta_out);
+    if (!flux || !mask || !zqso || !wav || !sums) return fail(QFA_ERR_NULL, "NULL input");
+    const int P = Nb + Nr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(sums, 0, 2 * (size_t)P * sizeof(double), st));
+    if (N == 0) return 0;
+    const int gx = (P + 127) / 128;
+    int gy = (4 * num_sms() + gx - 1) / gx;
+    if (gy > N) gy = N;
+    aux::k_tau_weight_sums<<<dim3(gx, gy), 128, 0, st>>>(flux, mask, zqso, wav, N, Nb, P, aux::kNSeries, aux_law(tau_law), sums);
+    QFA_LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qfa_ood_select(const float* nll, int B, float threshold, int k, int thr_cap, int* count_out, int* thr_idx,
+                              int* top_idx, float* top_val, void* stream) {
+    if (B < 0 || k < 0 || thr_cap < 0) return fail(QFA_ERR_SHAPE, "B=%d k=%d cap=%d", B, k, thr_cap);
+    if (k > aux::kTopKMax) return fail(QFA_ERR_UNSUPPORTED, "k=%d: at most %d", k, aux::kTopKMax);
+    if (!nll && B > 0) return fail(QFA_ERR_NULL, "nll is NULL");
+    if (k > 0 && !top_idx) return fail(QFA_ERR_NULL, "top_idx is NULL");
+    if (!count_out && k == 0) return 0;
+    aux::k_ood_select<<<1, 1024, 0, (cudaStream_t)stream>>>(nll, B, threshold, k, thr_cap, count_out, thr_idx, top_idx, top_val);
+    QFA_LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qfa_sample_posterior(const QfaModel* model, const float* hmean, const float* hcov, int B, int S,
+                                    unsigned long long seed, float* z_out, float* h_out, float* cont_out, void* stream) {
+    int rc = check_model(model, QFA_PREC_FP32);
+    if (rc) return rc;
+    if (B < 0 || S < 0) return fail(QFA_ERR_SHAPE, "B=%d S=%d", B, S);
+    if (B == 0 || S == 0) return 0;
+    if (!hmean || !hcov) return fail(QFA_ERR_NULL, "hmean/hcov is NULL");
+    if (cont_out && !model->mu) return fail(QFA_ERR_NULL, "model->mu is NULL (continuum samples need the mean spectrum)");
+    aux::k_sample_posterior<<<B, 128, 0, (cudaStream_t)stream>>>(hmean, hcov, model->params, model->mu, B, model->Nh,
+                                                                 model->Nb + model->Nr, S, seed, z_out, h_out, cont_out);
+    QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }
@@ -788,7 +905,7 @@ extern "C" int qfa_selftest_umma(const float* A, const float* Bimg_hi, const flo
     if (!A || !Bimg_hi || !Bimg_lo || !D || !err_flag) return fail(QFA_ERR_NULL, "NULL argument");
     const int smem = 49152 + 1024;
     CK(cudaFuncSetAttribute(k_selftest_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_selftest_umma<<<1, 128, smem, (cudaStream_t)stream>>>(A, Bimg_hi, Bimg_lo, D, split, err_flag);
+    k_selftest_umma<<<1, 128, smem, (cudaStream_t)stream>>>(A, Bimg_hi, Bimg_lo, D, split, err_flag); QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }
@@ -828,7 +945,7 @@ extern "C" int qfa_selftest_tma2d(const float* src, int rows, int npix, int pitc
         return fail(QFA_ERR_ALIGN, "a tensor map needs a 16-byte aligned base and a row pitch that is a multiple of 16 bytes");
     CUtensorMap tm;
     if (int rc = encode_tile_map(&tm, src, rows, npix, pitch_px, TMA_ST_COLS, TMA_ST_ROWS)) return rc;
-    k_selftest_tma2d<<<1, 128, 0, (cudaStream_t)stream>>>(tm, out, x0, y0, err_flag);
+    k_selftest_tma2d<<<1, 128, 0, (cudaStream_t)stream>>>(tm, out, x0, y0, err_flag); QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }
@@ -845,13 +962,13 @@ extern "C" int qfa_bench_tma2d(const float* src, int rows, int npix, int pitch_p
     cudaStream_t st = (cudaStream_t)stream;
     if (box_w == 32) {
         CK(cudaFuncSetAttribute(k_bench_tma2d<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_bench_tma2d<32><<<num_sms(), 256, smem, st>>>(tm, rows, npix, sink, err_flag);
+        k_bench_tma2d<32><<<num_sms(), 256, smem, st>>>(tm, rows, npix, sink, err_flag); QFA_LAUNCHED();
     } else if (box_w == 64) {
         CK(cudaFuncSetAttribute(k_bench_tma2d<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_bench_tma2d<64><<<num_sms(), 256, smem, st>>>(tm, rows, npix, sink, err_flag);
+        k_bench_tma2d<64><<<num_sms(), 256, smem, st>>>(tm, rows, npix, sink, err_flag); QFA_LAUNCHED();
     } else if (box_w == 128) {
         CK(cudaFuncSetAttribute(k_bench_tma2d<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_bench_tma2d<128><<<num_sms(), 256, smem, st>>>(tm, rows, npix, sink, err_flag);
+        k_bench_tma2d<128><<<num_sms(), 256, smem, st>>>(tm, rows, npix, sink, err_flag); QFA_LAUNCHED();
     } else return fail(QFA_ERR_SHAPE, "box_w must be 32, 64 or 128");
     CK(cudaGetLastError());
     return 0;
@@ -861,7 +978,7 @@ extern "C" int qfa_bench_tma2d(const float* src, int rows, int npix, int pitch_p
 extern "C" int qfa_bench_ldg(const float* src, int rows, int npix, int pitch_px, float* sink, void* stream) {
     if (!src || !sink) return fail(QFA_ERR_NULL, "NULL argument");
     if (rows <= 0 || npix <= 0 || pitch_px < npix) return fail(QFA_ERR_SHAPE, "rows=%d npix=%d pitch=%d", rows, npix, pitch_px);
-    k_bench_ldg<<<num_sms(), 512, 0, (cudaStream_t)stream>>>(src, rows, npix, pitch_px, sink);
+    k_bench_ldg<<<num_sms(), 512, 0, (cudaStream_t)stream>>>(src, rows, npix, pitch_px, sink); QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }

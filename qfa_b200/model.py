@@ -10,17 +10,32 @@ State layout: the six trainable tensors live back to back in ONE float32 device
 buffer `self._params` = [F | Psi | omega | tau0 | c0 | beta]; `self.F`, ...,
 `self.beta` are views into it, so the fused Adam+clip kernel updates all of them
 with one launch and `save_to_npz` keeps the reference's .npz layout.
+
+Precision modes (constructor argument `precision`):
+  'fp32'  (DEFAULT) float arithmetic on the CUDA cores with the Nh x Nh algebra in double -- the
+          reference is a float32 program, this mode is at least as accurate as what it replaces and its
+          results do not depend on the batch size.
+  'fp64'  double everywhere: the parity mode (<= 1e-5 against the fp64-promoted reference).
+  'mixed' opt-in speed mode: above a per-path batch size (predict 1280, train step 512 / 192 spectra) the
+          contractions run on the tensor cores with TF32-rounded operands (continuum <= 1e-3); below it the
+          'fp32' kernels run.  NOTE: the same model therefore gives slightly different numbers for different
+          batch sizes (e.g. the last partial batch of an epoch), and the TF32 error grows with
+          cond(I + F^T W F) (high-S/N spectra).  'tf32' = always tensor cores; 'tf32x3' = tensor cores with
+          3xTF32 operand splitting (error ~1e-6).
 """
+import contextlib
 import ctypes
 import os
 import time
+import warnings
 from typing import Callable, Dict, Optional
 
 import numpy as np
 import torch
 
 from . import _lib
-from ._lib import QfaError, QfaModelStruct, PRECISIONS, FLAG_ZERO_ACC, FLAG_FORCE_TENSOR, FLAG_SOLVE_FP64
+from ._lib import (QfaError, QfaModelStruct, PRECISIONS, FLAG_ZERO_ACC, FLAG_FORCE_TENSOR, FLAG_SOLVE_FP64,
+                   FLAG_TF32X3)
 from .utils import default_tau, resolve_tau_law
 
 log2pi = 1.8378770664093453  # reference model.py:20
@@ -41,8 +56,9 @@ def _ptr(t: Optional[torch.Tensor]):
 class QFA(object):
 
     def __init__(self, Nb: int, Nr: int, Nh: int, device: torch.device, tau: Callable = default_tau,
-                 model_params: Dict[str, np.ndarray] = None, precision: str = "mixed") -> None:
-        """reference model.py:26-55 (+ `precision`: 'fp64' | 'fp32' | 'mixed')."""
+                 model_params: Dict[str, np.ndarray] = None, precision: str = "fp32") -> None:
+        """reference model.py:26-55 (+ `precision`: 'fp32' (default) | 'fp64' | 'mixed' | 'tf32' | 'tf32x3', see the module
+        docstring)."""
         self.Nb = int(Nb)
         self.Nr = int(Nr)
         self.Nh = int(Nh)
@@ -67,6 +83,10 @@ class QFA(object):
         self.process_group = None  # set by enable_data_parallel()
         self._dp = False
         self.solve_fp64 = False    # mixed mode, 8 < Nh <= 32: per-spectrum Cholesky in double instead of float
+        self.use_cuda_graph = True  # train(): replay the whole step as ONE captured CUDA graph when the loader allows it
+        self._graph = None
+        self._graph_key = None
+        self._loss_sum = None
         if model_params is not None:
             for k in _KEYS:
                 self._view(k).copy_(torch.as_tensor(np.asarray(model_params[k]), dtype=torch.float32))
@@ -148,6 +168,11 @@ class QFA(object):
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _on_device(self):
+        """Every C-ABI call runs with the model's device current: the library's launches, its per-device shared-memory
+        opt-ins and the stream handle all belong to it (a model on cuda:1 must work while cuda:0 is current)."""
+        return torch.cuda.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext()
+
     def _struct(self, need_mu=False):
         if need_mu and self._mu is None:
             raise QfaError("model.mu is not set (load_from_npz or train first)")
@@ -160,7 +185,8 @@ class QFA(object):
 
     @property
     def _flags(self):
-        return (FLAG_FORCE_TENSOR if self.precision == "tf32" else 0) | (FLAG_SOLVE_FP64 if self.solve_fp64 else 0)
+        return ((FLAG_FORCE_TENSOR if self.precision in ("tf32", "tf32x3") else 0)
+                | (FLAG_SOLVE_FP64 if self.solve_fp64 else 0) | (FLAG_TF32X3 if self.precision == "tf32x3" else 0))
 
     @property
     def _tdtype(self):
@@ -224,9 +250,11 @@ class QFA(object):
         nbytes = L.qfa_train_workspace_bytes(self.Nb, self.Nr, self.Nh, B, self._prec)
         ws = self._workspace(nbytes)
         st = self._struct()
-        _lib.check(L.qfa_train_accumulate(ctypes.byref(st), _ptr(delta), _ptr(error), _ptr(zabs), _ptr(mask), B,
-                                          _ptr(ws), ws.numel(), _ptr(self._acc), _ptr(nll_out), self._prec,
-                                          (FLAG_ZERO_ACC if zero else 0) | self._flags, self._stream()), "qfa_train_accumulate")
+        with self._on_device():
+            _lib.check(L.qfa_train_accumulate(ctypes.byref(st), _ptr(delta), _ptr(error), _ptr(zabs), _ptr(mask), B,
+                                              _ptr(ws), ws.numel(), _ptr(self._acc), _ptr(nll_out), self._prec,
+                                              (FLAG_ZERO_ACC if zero else 0) | self._flags, self._stream()),
+                       "qfa_train_accumulate")
         return self._acc
 
     def finalize(self, acc=None):
@@ -236,8 +264,9 @@ class QFA(object):
         if self._grads is None:
             self._grads = torch.empty(self.Nparams, dtype=torch.float32, device=self.device)
             self._loss = torch.empty(1, dtype=torch.float32, device=self.device)
-        _lib.check(L.qfa_grads_finalize(_ptr(acc), self.Nb, self.Nr, self.Nh, self._prec, _ptr(self._grads),
-                                        _ptr(self._loss), self._stream()), "qfa_grads_finalize")
+        with self._on_device():
+            _lib.check(L.qfa_grads_finalize(_ptr(acc), self.Nb, self.Nr, self.Nh, self._prec, _ptr(self._grads),
+                                            _ptr(self._loss), self._stream()), "qfa_grads_finalize")
         return self._loss.view(1, 1), self._as_dict(self._grads)
 
     def forward(self, delta: torch.Tensor, error: torch.Tensor, zabs: torch.Tensor, mask: torch.Tensor):
@@ -279,10 +308,11 @@ class QFA(object):
         B = flux.shape[0]
         st = self._struct(need_mu=True)
         ws = self._workspace(L.qfa_predict_workspace_bytes(self.Nb, self.Nr, self.Nh, B, self._prec))
-        _lib.check(L.qfa_predict(ctypes.byref(st), _ptr(flux), _ptr(error), _ptr(zabs), _ptr(mask), B, _ptr(ws),
-                                 ws.numel(), _ptr(out["nll"]), _ptr(out.get("hmean")), _ptr(out.get("hcov")),
-                                 _ptr(out.get("cont")), _ptr(out.get("unc")), self._prec, self._flags, self._stream()),
-                   "qfa_predict")
+        with self._on_device():
+            _lib.check(L.qfa_predict(ctypes.byref(st), _ptr(flux), _ptr(error), _ptr(zabs), _ptr(mask), B, _ptr(ws),
+                                     ws.numel(), _ptr(out["nll"]), _ptr(out.get("hmean")), _ptr(out.get("hcov")),
+                                     _ptr(out.get("cont")), _ptr(out.get("unc")), self._prec, self._flags, self._stream()),
+                       "qfa_predict")
 
     # ------------------------------------------------------------------ host-buffer (end-to-end) paths
     def _host_pipeline(self, arrays, chunk, body):
@@ -410,11 +440,15 @@ class QFA(object):
                                   dtype=torch.float32)
         Niter = dataloader.data_size // dataloader.batch_size      # quirk Q8: under-counts a partial batch
         fused = hasattr(optimizer, "update_from_acc")
+        graphed = (fused and self.use_cuda_graph and self.device.type == "cuda" and hasattr(dataloader, "graph_batch")
+                   and hasattr(optimizer, "update_from_acc_dev") and Niter > 0)
 
         def step(i):
             dataloader.rewind()
             start_time = time.time()
-            if fused:
+            if graphed:
+                total_loss = self._graphed_epoch(optimizer, dataloader, Niter)
+            elif fused:
                 total = torch.zeros((), dtype=torch.float64, device=self.device)
                 while dataloader.have_next_batch():
                     d, e, z, m = dataloader.next_batch()
@@ -456,13 +490,122 @@ class QFA(object):
         o = self.Nparams + self.Npix + 3
         return (acc[o] / acc[o + 1]).to(torch.float64)
 
+    # ------------------------------------------------------------------ CUDA-graph train step
+    def capture_train_step(self, optimizer, dataloader, Niter):
+        """Captures ONE train step -- gather + delta of the next shuffled batch (qfa_gather_prepare, device cursor), the
+        accumulation kernels, the all-reduce of `acc` (NCCL, when data parallel), the fused Adam + clip update, the loss
+        bookkeeping and the cursor advance -- into a CUDA graph.  Nothing in it takes a host-side argument: the
+        epoch-dependent scalars are read from the optimizer's device buffer, so the same graph serves every epoch.
+        Reference loop being replaced: model.py:206-215 + optimizer.py:47-52."""
+        bufs, cursor = dataloader.graph_batch()
+        B = int(bufs[0].shape[0])
+        key = (B, self.precision, id(optimizer), id(dataloader), Niter, self._dp)
+        if self._graph is not None and self._graph_key == key:
+            return self._graph
+        if self._loss_sum is None:
+            self._loss_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        optimizer.sync_hyper(self)
+        # warm-up outside the capture: allocates workspace / acc and performs the library's one-off per-device set-up
+        cur0 = cursor.clone()
+        dataloader.graph_fill()
+        self.accumulate(*bufs, zero=True)
+        cursor.copy_(cur0)
+        torch.cuda.synchronize(self.device)
+        L = _lib.lib()
+        n0 = L.qfa_launch_count()
+        g = torch.cuda.CUDAGraph()
+        with self._on_device(), torch.cuda.graph(g):
+            dataloader.graph_fill()
+            acc = self.accumulate(*bufs, zero=True)
+            self._allreduce(acc)
+            optimizer.update_from_acc_dev(self, acc, self._loss_sum, 1.0 / Niter, cursor, B)
+        self.graph_launches_per_step = int(L.qfa_launch_count() - n0)
+        self._graph, self._graph_key = g, key
+        return g
+
+    def _graphed_epoch(self, optimizer, dataloader, Niter):
+        """One epoch with the captured step; a trailing partial batch runs eagerly through the same kernels."""
+        g = self.capture_train_step(optimizer, dataloader, Niter)
+        optimizer.sync_hyper(self)
+        self._loss_sum.zero_()
+        n_full = dataloader.graph_full_batches_left()
+        for _ in range(n_full):
+            g.replay()
+        dataloader.graph_advance(n_full)
+        while dataloader.have_next_batch():
+            d, e, z, m = dataloader.next_batch()
+            acc = self.accumulate(d, e, z, m, zero=True)
+            self._allreduce(acc)
+            optimizer.update_from_acc_dev(self, acc, self._loss_sum, 1.0 / Niter, None, 0)
+        return float(self._loss_sum.item())
+
+    # ------------------------------------------------------------------ consumers of the prediction (SURVEY.md 8f row 3)
+    def ood_select(self, nll, threshold=None, k=0, cap=None):
+        """Out-of-distribution scoring on per-spectrum NLLs (device tensor, e.g. from nll_batch): entirely on the device.
+        Returns dict(count = #(nll > threshold) [0-d int tensor], above = indices of up to `cap` of them (sorted),
+        top_idx / top_val = the k largest NLLs, descending)."""
+        self._require_cuda()
+        nll = torch.as_tensor(nll).to(self.device, torch.float32).contiguous()
+        B = nll.numel()
+        L = _lib.lib()
+        dev = self.device
+        out = {}
+        count = torch.zeros(1, dtype=torch.int32, device=dev) if threshold is not None else None
+        cap = (B if cap is None else int(cap)) if threshold is not None else 0
+        thr_idx = torch.empty(max(cap, 1), dtype=torch.int32, device=dev) if threshold is not None else None
+        k = min(int(k), B)
+        top_idx = torch.empty(max(k, 1), dtype=torch.int32, device=dev) if k > 0 else None
+        top_val = torch.empty(max(k, 1), dtype=torch.float32, device=dev) if k > 0 else None
+        with self._on_device():
+            _lib.check(L.qfa_ood_select(_ptr(nll), B, float(threshold) if threshold is not None else 0.0, k, cap,
+                                        _ptr(count), _ptr(thr_idx), _ptr(top_idx), _ptr(top_val), self._stream()),
+                       "qfa_ood_select")
+        if threshold is not None:
+            out["count"] = count[0]
+            n = torch.clamp(count[0], max=cap)
+            out["above"] = torch.sort(thr_idx[:int(n.item())]).values.to(torch.int64)
+        if k > 0:
+            out["top_idx"], out["top_val"] = top_idx[:k].to(torch.int64), top_val[:k]
+        return out
+
+    def sample_posterior(self, hmean, hcov, n_samples=20, seed=0, want=("h", "cont")):
+        """nb/predict.ipynb cell 11 on the device, batched: h ~ N(hmean, hcov) and the continuum samples mu + F h.
+        hmean (B,Nh), hcov (B,Nh,Nh) as predict_batch returns them.  Returns dict(h (B,S,Nh), cont (B,S,Npix), z)."""
+        self._require_cuda()
+        hmean = torch.as_tensor(hmean).to(self.device, torch.float32).reshape(-1, self.Nh).contiguous()
+        hcov = torch.as_tensor(hcov).to(self.device, torch.float32).reshape(-1, self.Nh, self.Nh).contiguous()
+        B, S = hmean.shape[0], int(n_samples)
+        out = {"z": torch.empty(B, S, self.Nh, device=self.device), "h": torch.empty(B, S, self.Nh, device=self.device)}
+        if "cont" in want:
+            out["cont"] = torch.empty(B, S, self.Npix, device=self.device)
+        st = self._struct(need_mu="cont" in want)
+        with self._on_device():
+            _lib.check(_lib.lib().qfa_sample_posterior(ctypes.byref(st), _ptr(hmean), _ptr(hcov), B, S, int(seed),
+                                                       _ptr(out["z"]), _ptr(out["h"]), _ptr(out.get("cont")), self._stream()),
+                       "qfa_sample_posterior")
+        return out
+
+    def predict_to_npz(self, path, flux, error, zabs, mask, names=None, chunk=8192):
+        """Batched replacement of the predict loop of reference main.py:94-98 (one .npz PER SPECTRUM with keys ll, hmean,
+        hcov, cont, uncertainty): the host arrays stream through predict_host and ONE columnar .npz is written with the
+        same five keys, each with a leading spectrum axis (+ `names` if given)."""
+        o = self.predict_host(torch.as_tensor(flux), torch.as_tensor(error), torch.as_tensor(zabs), torch.as_tensor(mask),
+                              chunk=chunk)
+        cols = {"ll": o["nll"].numpy(), "hmean": o["hmean"].numpy(), "hcov": o["hcov"].numpy(), "cont": o["cont"].numpy(),
+                "uncertainty": o["unc"].numpy()}
+        if names is not None:
+            cols["names"] = np.asarray(names)
+        np.savez(path, **cols)
+        return cols
+
     # ------------------------------------------------------------------ housekeeping
     def clip(self):
         """reference model.py:233-241"""
         if self.device.type == "cuda":
             L = _lib.lib()
-            _lib.check(L.qfa_clip(_ptr(self._params), self.Nb, self.Nr, self.Nh, self.min_value, self.max_value,
-                                  self._stream()), "qfa_clip")
+            with self._on_device():
+                _lib.check(L.qfa_clip(_ptr(self._params), self.Nb, self.Nr, self.Nh, self.min_value, self.max_value,
+                                      self._stream()), "qfa_clip")
         else:   # host-side bookkeeping only (tests of the container logic); not a compute fallback
             self._view("omega").clamp_(self.min_value, self.max_value)
             self._view("Psi").clamp_(self.min_value, self.max_value)
@@ -475,8 +618,9 @@ class QFA(object):
         if self.device.type == "cuda":
             L = _lib.lib()
             out = torch.empty_like(self._params)
-            _lib.check(L.qfa_smooth(_ptr(self._params), _ptr(out), self.Nb, self.Nr, self.Nh, self._stream()),
-                       "qfa_smooth")
+            with self._on_device():
+                _lib.check(L.qfa_smooth(_ptr(self._params), _ptr(out), self.Nb, self.Nr, self.Nh, self._stream()),
+                           "qfa_smooth")
             self._params.copy_(out)
         else:
             import torch.nn.functional as Fn
@@ -487,18 +631,28 @@ class QFA(object):
             self.omega, self.Psi, self.F = om, ps, Fs
 
     def save_to_npz(self, output_dir: str, file_name: str):
-        """reference model.py:254-280: keys mu,F,Psi,omega,tau0,c0,beta, all float32."""
+        """reference model.py:254-280: keys mu,F,Psi,omega,tau0,c0,beta, all float32 -- plus one extra key `qfa_b200`
+        (the ABI version) that marks the file as written by this package: load_from_npz then restores the stored c0
+        instead of applying the reference's c0 <- beta quirk, so checkpoints round-trip.  The reference's own loader
+        reads by key and ignores the extra entry."""
         mu = self._mu.cpu().detach().numpy()
         host = {k: self._view(k).cpu().detach().numpy() for k in _KEYS}
         if not os.path.exists(output_dir):
             os.mkdir(output_dir)
-        np.savez(os.path.join(output_dir, file_name), mu=mu, **host)
+        np.savez(os.path.join(output_dir, file_name), mu=mu, qfa_b200=np.int32(_lib.ABI_VERSION), **host)
 
-    def load_from_npz(self, path: str, reference_c0_bug: bool = True):
-        """reference model.py:282-295.  The reference assigns c0 <- file['beta'] (model.py:295,
-        quirk Q1) and its shipped golden vector only reproduces with that behaviour, so it is
-        the default; pass reference_c0_bug=False to load the stored c0."""
+    def load_from_npz(self, path: str, reference_c0_bug: Optional[bool] = None):
+        """reference model.py:282-295.  The reference assigns c0 <- file['beta'] (model.py:295, quirk Q1) and its
+        shipped golden vector only reproduces with that behaviour.  reference_c0_bug=None (default): files written by
+        the REFERENCE (no `qfa_b200` marker, e.g. data/model_parameters.npz) are loaded exactly like the reference loads
+        them -- with the quirk, and a warning when it changes the value -- while files written by this package's
+        save_to_npz / train() restore their stored c0.  True / False force either behaviour."""
         file = np.load(path)
+        if reference_c0_bug is None:
+            reference_c0_bug = "qfa_b200" not in file.files
+            if reference_c0_bug and float(file["c0"]) != float(file["beta"]):
+                warnings.warn(f"{path}: loaded like the reference does (model.py:295): c0 <- beta = {float(file['beta']):.6g}, "
+                              f"the stored c0 = {float(file['c0']):.6g} is ignored; pass reference_c0_bug=False to use it")
         self.mu = torch.tensor(file['mu'], dtype=torch.float32)
         for k in ("F", "omega", "Psi", "tau0", "beta"):
             self._view(k).copy_(torch.tensor(file[k], dtype=torch.float32))

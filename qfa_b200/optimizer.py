@@ -72,11 +72,12 @@ class Adam(object):
         bias1 = 1. - self.b1 ** (self.i + 1)
         bias2 = 1. - self.b2 ** (self.i + 1)
         st = ctypes.c_void_p(torch.cuda.current_stream(params_packed.device).cuda_stream)
-        _lib.check(L.qfa_adam_clip_step(_ptr(params_packed), _ptr(self._m), _ptr(self._v), _ptr(acc),
-                                        _ptr(grads_packed), model.Nb, model.Nr, model.Nh, model._prec,
-                                        self.scheduled_lr, self.b1, self.b2, self.eps, self.weight_decay,
-                                        bias1, bias2, model.min_value, model.max_value, st),
-                   "qfa_adam_clip_step")
+        with torch.cuda.device(params_packed.device):
+            _lib.check(L.qfa_adam_clip_step(_ptr(params_packed), _ptr(self._m), _ptr(self._v), _ptr(acc),
+                                            _ptr(grads_packed), model.Nb, model.Nr, model.Nh, model._prec,
+                                            self.scheduled_lr, self.b1, self.b2, self.eps, self.weight_decay,
+                                            bias1, bias2, model.min_value, model.max_value, st),
+                       "qfa_adam_clip_step")
 
     def update_from_acc(self, model, acc):
         """forward -> (all-reduce) -> update without materialising the gradient:
@@ -84,6 +85,31 @@ class Adam(object):
         if self._m is None:
             self.reset(model.parameters)
         self._fused(model, model._params, acc=acc)
+
+    def sync_hyper(self, model):
+        """Device copy of the epoch-dependent scalars {lr_i, 1 - b1^(i+1), 1 - b2^(i+1)} (optimizer.py:50-52,98) that
+        qfa_adam_clip_step_dev reads: refreshed once per epoch, so a captured CUDA graph never goes stale."""
+        if self._m is None:
+            self.reset(model.parameters)
+        vals = [self.scheduled_lr, 1. - self.b1 ** (self.i + 1), 1. - self.b2 ** (self.i + 1)]
+        if getattr(self, "_hyper", None) is None or self._hyper.device != model._params.device:
+            self._hyper = torch.zeros(3, dtype=torch.float32, device=model._params.device)
+        self._hyper.copy_(torch.tensor(vals, dtype=torch.float32))
+        return self._hyper
+
+    def update_from_acc_dev(self, model, acc, loss_sum=None, loss_scale=0.0, cursor=None, cursor_step=0):
+        """update_from_acc with the scalars read from the device (graph-capturable); optionally accumulates the step's
+        mean NLL * loss_scale into `loss_sum` (double[1]) and advances the loader's device cursor."""
+        if getattr(self, "_hyper", None) is None:
+            self.sync_hyper(model)
+        L = _lib.lib()
+        st = ctypes.c_void_p(torch.cuda.current_stream(model._params.device).cuda_stream)
+        with torch.cuda.device(model._params.device):
+            _lib.check(L.qfa_adam_clip_step_dev(_ptr(model._params), _ptr(self._m), _ptr(self._v), _ptr(acc), model.Nb,
+                                                model.Nr, model.Nh, model._prec, _ptr(self._hyper), self.b1, self.b2,
+                                                self.eps, self.weight_decay, model.min_value, model.max_value,
+                                                _ptr(loss_sum), float(loss_scale), _ptr(cursor), int(cursor_step), st),
+                       "qfa_adam_clip_step_dev")
 
     def update(self, params, g):
         """reference optimizer.py:37-52 (functional signature: returns the updated dict)."""
@@ -95,12 +121,18 @@ class Adam(object):
             out.packed, out.clipped = pp, True
             out.model = model
             return out
-        g = {v: g[v] + self.weight_decay * params[v] for v in g}
-        self.m = {v: (1 - self.b1) * g[v] + self.b1 * self.m[v] for v in g}
-        self.v = {k: (1 - self.b2) * g[k] * g[k] + self.b2 * self.v[k] for k in g}
-        mhat = {v: self.m[v] / (1. - self.b1 ** (self.i + 1)) for v in g}
-        vhat = {k: self.v[k] / (1. - self.b2 ** (self.i + 1)) for k in g}
-        return {v: params[v] - self.scheduled_lr * mhat[v] / (torch.sqrt(vhat[v]) + self.eps) for v in params}
+        # dicts of ordinary tensors (API compatibility; the hot path is the fused kernel above): same arithmetic as
+        # oracle.qfa_dense.adam_update -- L2 term, moment EMAs, bias correction by the epoch counter, step
+        t = self.i + 1
+        c1, c2 = 1. - self.b1 ** t, 1. - self.b2 ** t
+        lr = self.scheduled_lr
+        out = {}
+        for name, p in params.items():
+            grad = g[name] + self.weight_decay * p
+            self.m[name] = (1. - self.b1) * grad + self.b1 * self.m[name]
+            self.v[name] = (1. - self.b2) * (grad * grad) + self.b2 * self.v[name]
+            out[name] = p - lr * (self.m[name] / c1) / (torch.sqrt(self.v[name] / c2) + self.eps)
+        return out
 
 
 def step_scheduler(alpha: float, step: int) -> Callable[[int, float], float]:

@@ -24,10 +24,18 @@ LAW_CONSTANTS = {
     "mock": (0.2231435513142097, 3.2, 0.0, 3.25),
 }
 
-# Lyman series (oscillator strength f, wavelength): reference QFA/Lyman_series.csv, first 5 lines
-# are all any grid redward of 930 A can need; coefficient = lambda*f / (lambda*f)_alpha (utils.py:146-147)
-_LYMAN = [(4.1620e-01, 1215.6701), (7.9140e-02, 1025.7222), (2.9010e-02, 972.5367),
-          (1.3950e-02, 949.7430), (7.8030e-03, 937.8034)]
+# Lyman series (oscillator strength f, wavelength in Angstrom): the atomic data of reference QFA/Lyman_series.csv
+# (30 lines, Ly-alpha .. n = 31); coefficient = lambda*f / (lambda*f)_alpha (utils.py:146-147).  Same table as the
+# kernels' (csrc/qfa_aux.cuh).
+_LYMAN = [
+    (4.1620e-01, 1215.6701), (7.9140e-02, 1025.7222), (2.9010e-02, 972.5367), (1.3950e-02, 949.7430),
+    (7.8030e-03, 937.8034), (4.8160e-03, 930.7482), (3.1850e-03, 926.2256), (2.2170e-03, 923.1503),
+    (1.6060e-03, 920.9630), (1.2010e-03, 919.3513), (9.2190e-04, 918.1293), (7.2310e-04, 917.1805),
+    (5.7770e-04, 916.4291), (4.6890e-04, 915.8238), (3.8580e-04, 915.3289), (3.2120e-04, 914.9192),
+    (2.7030e-04, 914.5762), (2.2970e-04, 914.2861), (1.9680e-04, 914.0385), (1.6990e-04, 913.8256),
+    (1.4770e-04, 913.6411), (1.2930e-04, 913.4803), (1.1370e-04, 913.3391), (1.0060e-04, 913.2146),
+    (8.9360e-05, 913.1042), (7.9780e-05, 913.0059), (7.1480e-05, 912.9179), (6.4350e-05, 912.8389),
+    (5.8120e-05, 912.7676), (5.2640e-05, 912.7032)]
 
 
 def series_coeff(series: int) -> float:
@@ -48,6 +56,24 @@ def tau(z, which: Optional[str] = "becker", series: Optional[int] = 1):
 
 
 default_tau = partial(tau, which="becker")  # reference model.py:21
+
+
+def tau_total(wav_grid, zqso, which: Optional[str] = "becker"):
+    """Total Lyman-series optical depth on the blue side, same call signature and result as reference
+    utils.py:174-203 (numpy in, numpy (N, Nb) out).  Host-side helper; the device path is qfa_gather_prepare."""
+    wav_grid = np.asarray(wav_grid, dtype=np.float64)
+    zqso = np.asarray(zqso, dtype=np.float64).reshape(-1)
+    if not wav_grid[0] < _LYMAN[0][1]:
+        raise ValueError("Wavelength grid does not cover Lyman series lines")
+    Nb = int(np.sum(wav_grid < _LYMAN[0][1]))
+    taus = np.zeros((len(zqso), Nb))
+    for s, (_, lam) in enumerate(_LYMAN):
+        if not wav_grid[0] < lam:
+            break
+        nb = int(np.sum(wav_grid < lam))
+        zabs = (zqso + 1).reshape(-1, 1) * wav_grid[:nb] / lam - 1
+        taus[:, :nb] += tau(zabs, which=which, series=s + 1)
+    return taus
 
 
 def tauHI(z, tau0, beta):

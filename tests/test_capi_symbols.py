@@ -11,8 +11,8 @@ from conftest import ROOT
 from qfa_b200 import _lib
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "qfa_b200.h")).read()
+def declared_symbols(header="qfa_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(qfa_[a-z0-9_]+)\s*\(", text)))
 
@@ -25,11 +25,18 @@ def test_header_symbols_are_bound_and_exported():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for n in names:
         assert hasattr(L, n), n
+    # the test / design / trace entry points live in their own header, not in the reference-facing one
+    dbg = declared_symbols("qfa_b200_debug.h")
+    assert set(dbg) == set(_lib.DEBUG_SIGNATURES), set(dbg) ^ set(_lib.DEBUG_SIGNATURES)
+    assert not set(dbg) & set(names)
+    for n in dbg:
+        assert hasattr(L, n), n
+    assert not any("selftest" in n or "bench" in n or "debug" in n for n in names)
 
 
 def test_host_side_entry_points_without_gpu():
     L = _lib.lib()
-    assert L.qfa_abi_version() == 1
+    assert L.qfa_abi_version() == 2
     assert L.qfa_param_len(720, 1193, 8) == 1913 * 8 + 1913 + 720 + 3          # reference model.py:42
     assert L.qfa_acc_len(720, 1193, 8) == 1913 * 8 + 1913 + 720 + 3 + 1913 + 3 + 2 + 1913
     assert L.qfa_train_workspace_bytes(720, 1193, 8, 500, 1) > 0
@@ -40,6 +47,10 @@ def test_host_side_entry_points_without_gpu():
     assert rc == -3
     with pytest.raises(_lib.QfaError):
         _lib.check(rc, "qfa_clip")
+    # the production build keeps no trace pointer: the debug setters refuse
+    assert L.qfa_debug_set_trace(None) == -8
+    assert L.qfa_launch_count() == 0
+    assert L.qfa_ood_select(None, 0, 0.0, 4096, 0, None, None, None, None, None) == -8
 
 
 def test_library_is_sm100a_only():
