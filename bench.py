@@ -63,8 +63,11 @@ WORKLOADS = {
                             global_batch=500),
     "sdss_train_tf32x3": dict(grid="sdss", Nh=8, kind="train", nspec=71_040, sample=64, baseline_config=3,
                               precision="tf32x3"),
+    "sdss100k_predict_tf32x3": dict(grid="sdss", Nh=8, kind="predict", nspec=100_000, sample=192, baseline_config=1,
+                                    precision="tf32x3"),
 }
-DEFAULT_ALSO = {1: ["sdss_train", "l32_train", "desi_score", "sdss_train_b8192", "sdss_train_b500", "sdss_train_tf32x3"],
+DEFAULT_ALSO = {1: ["sdss_train", "l32_train", "desi_score", "sdss_train_b8192", "sdss_train_b500", "sdss_train_tf32x3",
+                    "sdss100k_predict_tf32x3"],
                 0: ["l32_train", "sdss_train_b8192", "sdss_train_b500"]}     # 0 = any N > 1
 
 
@@ -351,6 +354,9 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- GPU arm
 def kernel_names(kind, Nh, precision):
+    if precision == "tf32x3":
+        return ("k_tc_gram_x3<TRAIN> (tcgen05, 3xTF32) + k_grad<float> (CUDA cores) + k_reduce + k_adam"
+                if kind in ("train", "graph_train") else "k_tc_gram_x3<PREDICT> (tcgen05, 3xTF32 Gram GEMM + double solve + continuum GEMM)")
     tc = precision in ("mixed", "tf32", "tf32x3")
     if kind in ("train", "graph_train"):
         if tc and Nh <= 8:

@@ -14,6 +14,7 @@
 #include "qfa_tc_gram.cuh"
 #include "qfa_tc_grad.cuh"
 #include "qfa_tc_gram32.cuh"
+#include "qfa_tc_gram_x3.cuh"
 
 using namespace qfa;
 
@@ -290,11 +291,46 @@ static Tc32Plan plan_tc32(int Nb, int Nr, int Nh, int B) {
     return p;
 }
 
+// ---- 3xTF32 path (QFA_FLAG_TF32X3, Nh <= 8): k_tc_gram_x3 (+ k_grad<float, 8> + k_reduce for the train step)
+struct TcX3Plan {
+    int nkb, npt, ntiles, nsplit, ntiles_blue;
+    tcg::TileSched ts;
+    size_t off_pb, off_qa, off_small, off_hasblue, off_nll, off_part, off_spart, total;
+};
+static TcX3Plan plan_tc_x3(int Nb, int Nr, int Nh, int B, bool train) {
+    TcX3Plan p;
+    const int P = Nb + Nr;
+    p.nkb = (P + tcx::XKB - 1) / tcx::XKB;
+    p.npt = (P + tcg::PT - 1) / tcg::PT;
+    p.ts = tile_sched(B, 8, &p.ntiles);
+    p.ntiles_blue = (Nb + 127) / 128;
+    int want = (4 * num_sms() + p.npt - 1) / p.npt;
+    if (want > B) want = B;
+    if (want < 1) want = 1;
+    p.nsplit = want;
+    const size_t Bn = B > 0 ? B : 1;
+    size_t o = 0;
+    p.off_pb = o; o = align_up(o + (size_t)p.nkb * tcx::XPB_TILE, 1024);
+    p.off_qa = o; o = align_up(o + (size_t)p.npt * tcx::XQA_TILE, 1024);
+    p.off_small = p.off_hasblue = p.off_nll = p.off_part = p.off_spart = o;
+    if (train) {
+        p.off_small = o;   o = align_up(o + Bn * SmallLayout<8>::len * 4, 256);
+        p.off_hasblue = o; o = align_up(o + Bn * 4, 256);
+        p.off_nll = o;     o = align_up(o + Bn * 4, 256);
+        p.off_part = o;    o = align_up(o + (size_t)p.nsplit * part_len(P, Nb, Nh) * 4, 256);
+        p.off_spart = o;   o = align_up(o + (size_t)p.nsplit * p.npt * 3 * 4, 256);
+    }
+    p.total = o + 256;
+    return p;
+}
+
 extern "C" size_t qfa_train_workspace_bytes(int Nb, int Nr, int Nh, int B, int precision) {
     if (Nb < 0 || Nr < 0 || Nb + Nr <= 0 || Nh < 1 || Nh > 32 || B < 0) return 0;
     size_t cc = plan_train(Nb, Nr, Nh, B, precision).total;
     if (tc_eligible(Nh, precision)) {
         size_t tc = plan_tc_train(Nb, Nr, Nh, B).total;
+        size_t x3 = plan_tc_x3(Nb, Nr, Nh, B, true).total;
+        if (x3 > tc) tc = x3;
         return tc > cc ? tc : cc;
     }
     if (tc32_eligible(Nh, precision)) {
@@ -306,7 +342,10 @@ extern "C" size_t qfa_train_workspace_bytes(int Nb, int Nr, int Nh, int B, int p
 
 extern "C" size_t qfa_predict_workspace_bytes(int Nb, int Nr, int Nh, int B, int precision) {
     if (Nb < 0 || Nr < 0 || Nb + Nr <= 0 || Nh < 1 || Nh > 32 || B < 0) return 0;
-    if (tc_eligible(Nh, precision)) return plan_tc(Nb, Nr, B, true).total;
+    if (tc_eligible(Nh, precision)) {
+        size_t a = plan_tc(Nb, Nr, B, true).total, b = plan_tc_x3(Nb, Nr, Nh, B, false).total;
+        return a > b ? a : b;
+    }
     return 256;
 }
 
@@ -528,6 +567,62 @@ static int train_accumulate_tc32(const QfaModel* m, const float* delta, const fl
     return 0;
 }
 
+static int x3_build_and_gram(const QfaModel* m, const float* x, const float* error, const float* zabs, const uint8_t* mask,
+                             int B, char* ws, const TcX3Plan& pl, bool train, bool want_o, tcx::TcGramX3Args& a, cudaStream_t st) {
+    using namespace tcx;
+    float* PB = reinterpret_cast<float*>(ws + pl.off_pb);
+    float* QA = reinterpret_cast<float*>(ws + pl.off_qa);
+    const int P = m->Nb + m->Nr;
+    const size_t n_el = (size_t)pl.nkb * tcg::PB_ROWS * XKB + (want_o ? (size_t)pl.npt * XQA_BLK * tcg::PT * XKB : 0);
+    int blocks = (int)((n_el + 255) / 256);
+    if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+    k_tc_build_images_x3<<<blocks, 256, 0, st>>>(m->params, P, m->Nh, PB, pl.nkb, want_o ? QA : nullptr, want_o ? pl.npt : 0);
+    QFA_LAUNCHED();
+    CK(cudaGetLastError());
+    static PerDeviceOnce attr_once;
+    if (!attr_once.done[current_device()]) {
+        CK(cudaFuncSetAttribute(k_tc_gram_x3<tcg::TC_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, XCfg<tcg::TC_PREDICT>::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(k_tc_gram_x3<tcg::TC_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, XCfg<tcg::TC_TRAIN>::SMEM_BYTES));
+        attr_once.done[current_device()] = true;
+    }
+    a.f = make_field<float>(m, x, error, zabs, mask);
+    a.B = B; a.ts = pl.ts; a.ntiles = pl.ntiles; a.nkb = pl.nkb; a.npt = pl.npt; a.PB = PB; a.QA = QA;
+    int grid = pl.ntiles < num_sms() ? pl.ntiles : num_sms();
+    if (train) k_tc_gram_x3<tcg::TC_TRAIN><<<grid, tcg::NTHREADS, XCfg<tcg::TC_TRAIN>::SMEM_BYTES, st>>>(a);
+    else k_tc_gram_x3<tcg::TC_PREDICT><<<grid, tcg::NTHREADS, XCfg<tcg::TC_PREDICT>::SMEM_BYTES, st>>>(a);
+    QFA_LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// train step in 3xTF32 mode: Grams + solve on the tensor cores (k_tc_gram_x3<TRAIN>), gradient contraction by the float
+// CUDA-core kernel k_grad<float, 8> from the same hand-off record the 'fp32' mode uses
+static int train_accumulate_x3(const QfaModel* m, const float* delta, const float* error, const float* zabs,
+                               const uint8_t* mask, int B, char* ws, const TcX3Plan& pl, float* acc, float* nll_out,
+                               int flags, cudaStream_t st) {
+    const int P = m->Nb + m->Nr, Nb = m->Nb, Nh = m->Nh;
+    if (flags & QFA_FLAG_ZERO_ACC) CK(cudaMemsetAsync(acc, 0, qfa_acc_len(m->Nb, m->Nr, Nh) * sizeof(float), st));
+    if (B == 0) return 0;
+    float* small = reinterpret_cast<float*>(ws + pl.off_small);
+    float* hasblue = reinterpret_cast<float*>(ws + pl.off_hasblue);
+    float* nll = nll_out ? nll_out : reinterpret_cast<float*>(ws + pl.off_nll);
+    float* part = reinterpret_cast<float*>(ws + pl.off_part);
+    float* spart = reinterpret_cast<float*>(ws + pl.off_spart);
+    tcx::TcGramX3Args a;
+    a.nll = nll; a.hmean = nullptr; a.hcov = nullptr; a.cont = nullptr; a.unc = nullptr; a.small = small; a.hasblue = hasblue;
+    if (int rc = x3_build_and_gram(m, delta, error, zabs, mask, B, ws, pl, true, false, a, st)) return rc;
+    GradArgs<float> gr;
+    gr.f = a.f; gr.B = B; gr.nsplit = pl.nsplit; gr.small = small; gr.part = part; gr.spart = spart; gr.accumulate = 0;
+    CK(dispatch_grad<float>(8, gr, pl.npt, st));
+    ReduceArgs<float> ra;
+    ra.part = part; ra.spart = spart; ra.nll = nll; ra.hasblue = hasblue; ra.scal = a.f.scal;
+    ra.acc = acc; ra.P = P; ra.Nb = Nb; ra.Nh = Nh; ra.B = B; ra.stride = 1; ra.nsp = (double)B; ra.nsplit = pl.nsplit;
+    ra.ntiles_blue = pl.ntiles_blue; ra.ntiles = pl.npt; ra.nsplit_red = pl.nsplit; ra.tile_px = 128;
+    k_reduce<float><<<(int)((part_len(P, Nb, Nh) + 255) / 256), 256, 0, st>>>(ra); QFA_LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int qfa_train_accumulate(const QfaModel* model, const float* delta, const float* error,
                                     const float* zabs, const uint8_t* mask, int B, void* workspace,
                                     size_t workspace_bytes, void* acc, void* nll_per_spectrum, int precision,
@@ -543,6 +638,14 @@ extern "C" int qfa_train_accumulate(const QfaModel* model, const float* delta, c
         return fail(QFA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total, workspace_bytes);
     if (((uintptr_t)workspace & 255) != 0) return fail(QFA_ERR_ALIGN, "workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    if ((flags & QFA_FLAG_TF32X3) && precision == QFA_PREC_TF32) {
+        if (model->Nh > tcg::HP) return fail(QFA_ERR_UNSUPPORTED, "QFA_FLAG_TF32X3 is implemented for Nh <= 8 (Nh = %d)", model->Nh);
+        TcX3Plan xp = plan_tc_x3(model->Nb, model->Nr, model->Nh, B, true);
+        if (B > 0 && workspace_bytes < xp.total)
+            return fail(QFA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", xp.total, workspace_bytes);
+        return train_accumulate_x3(model, delta, error, zabs, mask, B, (char*)workspace, xp, (float*)acc,
+                                   (float*)nll_per_spectrum, flags, st);
+    }
     if (tc_use(model->Nh, precision, B, flags, TC_PATH_TRAIN)) {
         TcTrainPlan tp = plan_tc_train(model->Nb, model->Nr, model->Nh, B);
         if (B > 0 && workspace_bytes < tp.total)
@@ -617,6 +720,17 @@ extern "C" int qfa_predict(const QfaModel* model, const float* flux, const float
     if (!nll) return fail(QFA_ERR_NULL, "nll is NULL");
     if (!flux || !error || !mask || (!zabs && model->Nb > 0)) return fail(QFA_ERR_NULL, "flux/error/zabs/mask is NULL");
     cudaStream_t st = (cudaStream_t)stream;
+    if ((flags & QFA_FLAG_TF32X3) && precision == QFA_PREC_TF32) {
+        if (model->Nh > tcg::HP) return fail(QFA_ERR_UNSUPPORTED, "QFA_FLAG_TF32X3 is implemented for Nh <= 8 (Nh = %d)", model->Nh);
+        TcX3Plan xp = plan_tc_x3(model->Nb, model->Nr, model->Nh, B, false);
+        if (!workspace || workspace_bytes < xp.total)
+            return fail(QFA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", xp.total, workspace_bytes);
+        if (((uintptr_t)workspace & 255) != 0) return fail(QFA_ERR_ALIGN, "workspace must be 256-byte aligned");
+        tcx::TcGramX3Args a;
+        a.nll = (float*)nll; a.hmean = (float*)hmean; a.hcov = (float*)hcov; a.cont = (float*)cont; a.unc = (float*)unc;
+        a.small = nullptr; a.hasblue = nullptr;
+        return x3_build_and_gram(model, flux, error, zabs, mask, B, (char*)workspace, xp, false, cont || unc, a, st);
+    }
     if (tc_use(model->Nh, precision, B, flags, TC_PATH_PREDICT)) {
         const bool want_o = cont || unc;
         TcPlan pl = plan_tc(model->Nb, model->Nr, B, true);
