@@ -154,7 +154,7 @@ static inline bool tc_eligible(int Nh, int precision) { return precision == QFA_
 // below a path-specific batch size the float CUDA-core kernels (one CTA per spectrum) are faster.  Measured cross-overs on a
 // B200 (profiles/r1_small_batch.txt): predict ~1 200 spectra, train step Nh <= 8 ~500, train step 8 < Nh <= 32 ~170.
 // QFA_TC_MIN_BATCH (env) overrides all three; QFA_FLAG_FORCE_TENSOR forces the tensor-core kernels (tests, profiling).
-enum { TC_PATH_PREDICT = 0, TC_PATH_TRAIN = 1, TC_PATH_TRAIN32 = 2 };
+enum { TC_PATH_PREDICT = 0, TC_PATH_TRAIN = 1, TC_PATH_TRAIN32 = 2, TC_PATH_PREDICT32 = 3 };
 static int tc_min_batch(int path) {
     static int v = -2;
     if (v == -2) {
@@ -163,7 +163,7 @@ static int tc_min_batch(int path) {
         if (s && v < 0) v = 0;
     }
     if (v >= 0) return v;
-    return path == TC_PATH_PREDICT ? 1280 : (path == TC_PATH_TRAIN ? 512 : 192);
+    return path == TC_PATH_PREDICT ? 1280 : (path == TC_PATH_TRAIN ? 512 : (path == TC_PATH_TRAIN32 ? 192 : 640));
 }
 static inline bool tc_use(int Nh, int precision, int B, int flags, int path) {
     return tc_eligible(Nh, precision) && (B >= tc_min_batch(path) || (flags & QFA_FLAG_FORCE_TENSOR));
@@ -259,10 +259,10 @@ static TcTrainPlan plan_tc_train(int Nb, int Nr, int Nh, int B) {
 struct Tc32Plan {
     int nkb, ntiles, npix_tiles, nsplit, ntiles_blue;
     tcg::TileSched ts;
-    size_t off_pb, off_gram, off_small, off_hasblue, off_nll, off_part, off_spart, off_replay, total;
+    size_t off_pb, off_pb2, off_gram, off_small, off_hasblue, off_nll, off_part, off_spart, off_replay, total;
 };
 static inline bool tc32_eligible(int Nh, int precision) { return precision == QFA_PREC_TF32 && Nh > tcg::HP && Nh <= 32; }   // zero-padded to 32
-static Tc32Plan plan_tc32(int Nb, int Nr, int Nh, int B) {
+static Tc32Plan plan_tc32(int Nb, int Nr, int Nh, int B, bool predict = false) {
     Tc32Plan p;
     const int P = Nb + Nr;
     p.nkb = (P + tcg::KB - 1) / tcg::KB;
@@ -277,7 +277,8 @@ static Tc32Plan plan_tc32(int Nb, int Nr, int Nh, int B) {
     const size_t Bn = B > 0 ? B : 1;
     size_t o = 0;
     p.off_pb = o;      o = align_up(o + (size_t)p.nkb * tcg32::PB32_KB_BYTES + 16, 1024);
-    p.off_gram = o;    o = align_up(o + Bn * tcg32::G32_STRIDE * 4, 256);
+    p.off_pb2 = o;     o = align_up(o + (predict ? (size_t)p.nkb * tcg32::PB32_KB_BYTES + 16 : 0), 1024);   // residual image (3xTF32)
+    p.off_gram = o;    o = align_up(o + (predict ? 3 : 1) * Bn * tcg32::G32_STRIDE * 4, 256);
     p.off_small = o;   o = align_up(o + (Bn + 2) * tcg32::G32_IMG, 1024);      // per-spectrum images for k_tc_grad32 (+2: last step)
     p.off_hasblue = o; o = align_up(o + Bn * 4, 256);
     p.off_nll = o;     o = align_up(o + Bn * 4, 256);
@@ -346,6 +347,7 @@ extern "C" size_t qfa_predict_workspace_bytes(int Nb, int Nr, int Nh, int B, int
         size_t a = plan_tc(Nb, Nr, B, true).total, b = plan_tc_x3(Nb, Nr, Nh, B, false).total;
         return a > b ? a : b;
     }
+    if (tc32_eligible(Nh, precision)) return plan_tc32(Nb, Nr, Nh, B, true).total;
     return 256;
 }
 
@@ -530,11 +532,11 @@ static int train_accumulate_tc32(const QfaModel* m, const float* delta, const fl
     const size_t n_el = (size_t)pl.nkb * PB32_ROWS * tcg::KB;
     int blocks = (int)((n_el + 255) / 256);
     if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-    k_tc_build_images32<<<blocks, 256, 0, st>>>(m->params, P, Nh, PB, pl.nkb); QFA_LAUNCHED();
+    k_tc_build_images32<<<blocks, 256, 0, st>>>(m->params, P, Nh, PB, pl.nkb, 0); QFA_LAUNCHED();
     CK(cudaGetLastError());
     static PerDeviceOnce attr_once;
     if (!attr_once.done[current_device()]) {
-        CK(cudaFuncSetAttribute(k_tc_gram32, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM32_BYTES));
+        CK(cudaFuncSetAttribute(k_tc_gram32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM32_BYTES));
         CK(cudaFuncSetAttribute(k_solve32<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE32_SMEM));
         CK(cudaFuncSetAttribute(k_solve32<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE32_SMEM));
         CK(cudaFuncSetAttribute(k_tc_grad32, cudaFuncAttributeMaxDynamicSharedMemorySize, G32_SMEM));
@@ -545,7 +547,7 @@ static int train_accumulate_tc32(const QfaModel* m, const float* delta, const fl
     a.f = f; a.B = B; a.ts = pl.ts; a.ntiles = pl.ntiles; a.nkb = pl.nkb; a.PB = PB; a.gram = gram; a.trace = g_trace;
     a.replay = reinterpret_cast<float*>(ws + pl.off_replay);
     int grid = pl.ntiles < num_sms() ? pl.ntiles : num_sms();
-    k_tc_gram32<<<grid, tcg::NTHREADS, SMEM32_BYTES, st>>>(a); QFA_LAUNCHED();
+    k_tc_gram32<false><<<grid, tcg::NTHREADS, SMEM32_BYTES, st>>>(a); QFA_LAUNCHED();
     CK(cudaGetLastError());
     int sblocks = (B + SOLVE32_WARPS - 1) / SOLVE32_WARPS;
     if (sblocks > QFA_SOLVE32_CTAS * num_sms()) sblocks = QFA_SOLVE32_CTAS * num_sms();
@@ -708,6 +710,67 @@ static int predict_tc(const QfaModel* m, const float* flux, const float* error, 
     return 0;
 }
 
+// prediction for 8 < Nh <= 32 on the tensor cores: k_tc_gram32<PRED> (M, b) -> k_solve32<PRED> (NLL, hmean, hcov, [L^-1 | a]
+// images) -> k_out32 (continuum, 1-sigma)                                                      (model.py:160-180)
+static int predict_tc32(const QfaModel* m, const float* flux, const float* error, const float* zabs, const uint8_t* mask,
+                        int B, char* ws, const Tc32Plan& pl, float* nll, float* hmean, float* hcov, float* cont, float* unc,
+                        int flags, cudaStream_t st) {
+    using namespace tcg32;
+    const int P = m->Nb + m->Nr;
+    float* PB = reinterpret_cast<float*>(ws + pl.off_pb);
+    float* PBlo = reinterpret_cast<float*>(ws + pl.off_pb2);
+    float* gram = reinterpret_cast<float*>(ws + pl.off_gram);
+    float* img = reinterpret_cast<float*>(ws + pl.off_small);
+    const size_t n_el = (size_t)pl.nkb * PB32_ROWS * tcg::KB;
+    int blocks = (int)((n_el + 255) / 256);
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    k_tc_build_images32<<<blocks, 256, 0, st>>>(m->params, P, m->Nh, PB, pl.nkb, 0); QFA_LAUNCHED();
+    k_tc_build_images32<<<blocks, 256, 0, st>>>(m->params, P, m->Nh, PBlo, pl.nkb, 1); QFA_LAUNCHED();
+    CK(cudaGetLastError());
+    static PerDeviceOnce attr_once;
+    if (!attr_once.done[current_device()]) {
+        CK((cudaFuncSetAttribute(k_tc_gram32<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM32_BYTES)));
+        CK((cudaFuncSetAttribute(k_tc_gram32<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM32_BYTES)));
+        CK((cudaFuncSetAttribute(k_solve32<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE32_SMEM)));
+        CK((cudaFuncSetAttribute(k_solve32<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE32_SMEM)));
+        CK(cudaFuncSetAttribute(k_out32, cudaFuncAttributeMaxDynamicSharedMemorySize, G32_SMEM));
+        attr_once.done[current_device()] = true;
+    }
+    Field<float> f = make_field<float>(m, flux, error, zabs, mask);
+    // The per-spectrum outputs of a prediction do not average over a batch, and M = I + F^T W F of an Nh = 32 model is
+    // conditioned ~1e3: single-pass TF32 Grams put the continuum 1.6e-2 off (measured, scripts/p32_errors.py), above the 1e-3
+    // bar.  So the Grams are 3xTF32: hi*hi + lo*hi + hi*lo as three launches of the same kernel (operand part / image part),
+    // each into its own scratch row -- which also keeps the small cross terms out of the big accumulators (the tensor core's
+    // fp32 accumulation truncates) -- summed by k_solve32.
+    TcGram32Args a;
+    a.f = f; a.B = B; a.ts = pl.ts; a.ntiles = pl.ntiles; a.nkb = pl.nkb; a.trace = nullptr;
+    a.replay = reinterpret_cast<float*>(ws + pl.off_replay);
+    int grid = pl.ntiles < num_sms() ? pl.ntiles : num_sms();
+    const size_t gstride = (size_t)B * G32_STRIDE;
+    a.PB = PB; a.gram = gram;
+    k_tc_gram32<true, 0><<<grid, tcg::NTHREADS, SMEM32_BYTES, st>>>(a); QFA_LAUNCHED();
+    a.PB = PB; a.gram = gram + gstride;
+    k_tc_gram32<true, 1><<<grid, tcg::NTHREADS, SMEM32_BYTES, st>>>(a); QFA_LAUNCHED();
+    a.PB = PBlo; a.gram = gram + 2 * gstride;
+    k_tc_gram32<true, 0><<<grid, tcg::NTHREADS, SMEM32_BYTES, st>>>(a); QFA_LAUNCHED();
+    CK(cudaGetLastError());
+    int sblocks = (B + SOLVE32_WARPS - 1) / SOLVE32_WARPS;
+    if (sblocks > QFA_SOLVE32_CTAS * num_sms()) sblocks = QFA_SOLVE32_CTAS * num_sms();
+    if (flags & QFA_FLAG_SOLVE_FP64)
+        k_solve32<double, true><<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, img, nll, nullptr, hmean, hcov, m->Nh, 3);
+    else
+        k_solve32<float, true><<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, img, nll, nullptr, hmean, hcov, m->Nh, 3);
+    QFA_LAUNCHED();
+    CK(cudaGetLastError());
+    if (cont || unc) {
+        TcOut32Args o;
+        o.f = f; o.B = B; o.nsplit = pl.nsplit; o.img = img; o.cont = cont; o.unc = unc;
+        k_out32<<<dim3(pl.npix_tiles, pl.nsplit), G32_THREADS, G32_SMEM, st>>>(o); QFA_LAUNCHED();
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
 extern "C" int qfa_predict(const QfaModel* model, const float* flux, const float* error, const float* zabs,
                            const uint8_t* mask, int B, void* workspace, size_t workspace_bytes, void* nll,
                            void* hmean, void* hcov, void* cont, void* unc, int precision, int flags,
@@ -739,6 +802,17 @@ extern "C" int qfa_predict(const QfaModel* model, const float* flux, const float
         if (((uintptr_t)workspace & 255) != 0) return fail(QFA_ERR_ALIGN, "workspace must be 256-byte aligned");
         return predict_tc(model, flux, error, zabs, mask, B, (char*)workspace, pl, (float*)nll, (float*)hmean,
                           (float*)hcov, (float*)cont, (float*)unc, want_o, st);
+    }
+    // measured cross-overs against the float CUDA-core kernels (scripts/p32_errors.py): ~600 spectra for 16 < Nh <= 32, ~4500 for
+    // 8 < Nh <= 16 (whose CUDA-core kernel is the cheaper HP = 16 instance while the tensor path always pads to 32)
+    const int p32_min = tc_min_batch(TC_PATH_PREDICT32) * (model->Nh > 16 ? 1 : 7);
+    if (tc32_eligible(model->Nh, precision) && (B >= p32_min || (flags & QFA_FLAG_FORCE_TENSOR))) {
+        Tc32Plan tp = plan_tc32(model->Nb, model->Nr, model->Nh, B, true);
+        if (!workspace || workspace_bytes < tp.total)
+            return fail(QFA_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", tp.total, workspace_bytes);
+        if (((uintptr_t)workspace & 255) != 0) return fail(QFA_ERR_ALIGN, "workspace must be 256-byte aligned");
+        return predict_tc32(model, flux, error, zabs, mask, B, (char*)workspace, tp, (float*)nll, (float*)hmean, (float*)hcov,
+                            (float*)cont, (float*)unc, flags, st);
     }
     if (precision == QFA_PREC_FP64)
         return predict_t<double>(model, flux, error, zabs, mask, B, (double*)nll, (double*)hmean, (double*)hcov,

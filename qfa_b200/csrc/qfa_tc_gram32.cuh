@@ -77,7 +77,8 @@ __host__ __device__ constexpr int tri32(int k, int l) { return k * H32 - k * (k 
 __host__ __device__ constexpr int slice_cols(int p) { return p < 2 ? SLICE : NP2_32 - 2 * SLICE; }
 
 // static image: PB32[kb] = 560 rows x 32 pixels (SWIZZLE_128B rows, TF32-rounded); row n < 528 -> F_ik F_il, n = tri32(k,l)
-__global__ void k_tc_build_images32(const float* __restrict__ F, int P, int Nh, float* __restrict__ PB, int nkb) {
+// part = 0: TF32 (rna) image; part = 1: the residual image tf32(v - tf32(v)) for the 3xTF32 prediction Grams
+__global__ void k_tc_build_images32(const float* __restrict__ F, int P, int Nh, float* __restrict__ PB, int nkb, int part = 0) {
     const size_t n_el = (size_t)nkb * PB32_ROWS * KB;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += (size_t)gridDim.x * blockDim.x) {
         const int kappa = (int)(e % KB), row = (int)((e / KB) % PB32_ROWS), kb = (int)(e / (KB * PB32_ROWS));
@@ -93,13 +94,20 @@ __global__ void k_tc_build_images32(const float* __restrict__ F, int P, int Nh, 
                 v = __ldg(F + (size_t)i * Nh + (row - NP2_32));
             }
         }
-        PB[(size_t)kb * (PB32_KB_BYTES / 4) + sw128_offset(row, kappa) / 4] = tf32_rna(v);
+        const float hi = tf32_rna(v);
+        PB[(size_t)kb * (PB32_KB_BYTES / 4) + sw128_offset(row, kappa) / 4] = part == 0 ? hi : tf32_rna(v - hi);
     }
     if (blockIdx.x == 0 && threadIdx.x < 4) PB[(size_t)nkb * (PB32_KB_BYTES / 4) + threadIdx.x] = 0.f;   // 16 zero bytes (dummy mask)
 }
 
 // per-cell physics + operand generation; PASS0 also produces the wb / wb2 operands and the scalar sums
-template <int BLUE, bool PASS0>
+// PRED: prediction flavour (model.py:160-180): residual flux - mu A, only the s2 / wb operands (no second Gram)
+// PART (PRED only): 0 = the TF32 part of the generated operands, 1 = their residual tf32(v - tf32(v)) (3xTF32 prediction Grams)
+__device__ __forceinline__ float tf32_part(float v, int part) {
+    const float hi = tf32_rna(v);
+    return part == 0 ? hi : tf32_rna(v - hi);
+}
+template <int BLUE, bool PASS0, bool PRED = false, int PART = 0>
 __device__ __forceinline__ void compute_row32(const PhysConst& pc, const PixConst& px, const RowBuf& rb, bool blue, uint32_t sa,
                                               float& E, uint32_t& nbm, int j) {
     const bool mk = rb.m != 0u;
@@ -118,13 +126,13 @@ __device__ __forceinline__ void compute_row32(const PhysConst& pc, const PixCons
     const float w = rcpf(D);
     const float wA = w * A;
     const float s2 = wA * A;
-    sts_f32_imm<0>(sa, mk ? tf32_round(s2) : 0.0f);
-    if (BLUE != 0) sts_f32_imm<2 * A_TILE>(sa, mk ? tf32_round(s2 * A) : 0.0f);     // s3 (= s2 on red K-blocks)
+    sts_f32_imm<0>(sa, mk ? (PRED ? tf32_part(s2, PART) : tf32_round(s2)) : 0.0f);
+    if (BLUE != 0 && !PRED) sts_f32_imm<2 * A_TILE>(sa, mk ? tf32_round(s2 * A) : 0.0f);     // s3 (= s2 on red K-blocks)
     if (PASS0) {
-        const float r = rb.x;
+        const float r = PRED ? fmaf(-px.mu, A, rb.x) : rb.x;                        // model.py:166
         const float wb = wA * r;
-        sts_f32_imm<A_TILE>(sa, mk ? tf32_round(wb) : 0.0f);
-        if (BLUE != 0) {
+        sts_f32_imm<A_TILE>(sa, mk ? (PRED ? tf32_part(wb, PART) : tf32_round(wb)) : 0.0f);
+        if (BLUE != 0 && !PRED) {
             sts_f32_imm<3 * A_TILE>(sa, mk ? tf32_round(s2 * r) : 0.0f);            // wb2 (= wb on red K-blocks)
             nbm |= (mk && (BLUE == 1 || blue)) ? (1u << j) : 0u;
         }
@@ -133,13 +141,13 @@ __device__ __forceinline__ void compute_row32(const PhysConst& pc, const PixCons
     }
 }
 
-template <int BLUE, bool PASS0, int NR>
+template <int BLUE, bool PASS0, int NR, bool PRED = false, int PART = 0>
 __device__ __forceinline__ void kblock_consume32(const PhysConst& pc, const KBuf& kb, bool blue, uint32_t warp_sa, int nr,
                                                  float (&E)[RPW], uint32_t& nbm) {
 #pragma unroll
     for (int j = 0; j < RPW; ++j) {
         if (NR > 0 ? j < NR : j < nr)
-            compute_row32<BLUE, PASS0>(pc, kb.px, kb.r[j], blue, (warp_sa ^ ((uint32_t)j << 4)) + (uint32_t)j * 128u, E[j], nbm, j);
+            compute_row32<BLUE, PASS0, PRED, PART>(pc, kb.px, kb.r[j], blue, (warp_sa ^ ((uint32_t)j << 4)) + (uint32_t)j * 128u, E[j], nbm, j);
     }
 }
 
@@ -149,7 +157,7 @@ __device__ __forceinline__ void kblock_consume32(const PhysConst& pc, const KBuf
 // latency (period 6 200 cycles, 3 600 of them in the load phase).
 struct G32Worker {
     const float* x; const float* err; const float* zabs; const uint8_t* mask;   // row 0 of the tile
-    const float* Psi; const float* omega; const uint8_t* zero;
+    const float* Psi; const float* omega; const float* mu; const uint8_t* zero;
     int P, Nb, nkb, nr, warp, lane;
     uint32_t git0, ring_sa;
     uint64_t* bar_full; uint64_t* bar_empty;
@@ -157,10 +165,11 @@ struct G32Worker {
     long long* trace;
 };
 
+template <bool PRED, int PART>
 __device__ __noinline__ void gram32_pass0_worker(const G32Worker w, const PhysConst pc) {
     const int P = w.P, Nb = w.Nb, nkb = w.nkb, nr = w.nr, warp = w.warp, lane = w.lane;
     Field<float> f;
-    f.P = P; f.Nb = Nb; f.Psi = w.Psi; f.omega = w.omega; f.mu = nullptr;
+    f.P = P; f.Nb = Nb; f.Psi = w.Psi; f.omega = w.omega; f.mu = w.mu;
     float E[RPW];
     uint32_t nbm = 0u;
 #pragma unroll
@@ -183,8 +192,8 @@ __device__ __noinline__ void gram32_pass0_worker(const G32Worker w, const PhysCo
         constexpr bool PASS0 = true;
         auto load_kb = [&](int kb, KBuf& k) {
             const int p0 = kb * KB;
-            if (p0 + KB <= P) load_kblock<true, true, NR, true, true>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
-            else load_kblock<true, false, NR, true, true>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
+            if (p0 + KB <= P) load_kblock<!PRED, true, NR, true, true>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
+            else load_kblock<!PRED, false, NR, true, true>(f, tv, rc, p0, lane, nr, p0 < Nb, k);
         };
         load_kb(0, kA);
         if (nkb > 1) load_kb(1, kB);
@@ -200,9 +209,9 @@ __device__ __noinline__ void gram32_pass0_worker(const G32Worker w, const PhysCo
             if (tr) tr[1] = clock64();
             const uint32_t stage_sa = ring_sa + (uint32_t)s * (uint32_t)STAGE32_BYTES;
             const int bm = (p0 + KB <= Nb) ? 1 : (p0 >= Nb ? 0 : 2);
-            if (bm == 1) kblock_consume32<1, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
-            else if (bm == 0) kblock_consume32<0, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
-            else kblock_consume32<2, PASS0, NR>(pc, k, blue, stage_sa, nr, E, nbm);
+            if (bm == 1) kblock_consume32<1, PASS0, NR, PRED, PART>(pc, k, blue, stage_sa, nr, E, nbm);
+            else if (bm == 0) kblock_consume32<0, PASS0, NR, PRED, PART>(pc, k, blue, stage_sa, nr, E, nbm);
+            else kblock_consume32<2, PASS0, NR, PRED, PART>(pc, k, blue, stage_sa, nr, E, nbm);
             if (tr) tr[2] = clock64();
             fence_proxy_async_writer();     // MEMBAR.ALL.CTA: before the prefetch below, never after it
             __syncwarp();
@@ -238,6 +247,8 @@ struct TcGram32Args {
     long long* trace;      // debug (-DQFA_ENABLE_TRACE): CTA 0, first tile, pass 0: [kb][warp][4] clock64 stamps
 };
 
+// PRED = true: prediction flavour -- M and b only (the s3 / wb2 operands, their MMAs, replay copies and drains are skipped)
+template <bool PRED, int PART = 0>
 __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* ring = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -320,9 +331,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                                 const uint64_t ko = (uint64_t)(2 * kk);
                                 const bool acc = (kb | kk) != 0;
                                 umma_tf32(tmem + T_A, dS2 + ko, dP + ko, idA, acc);
-                                umma_tf32(tmem + T_C, dS3 + ko, dP + ko, idA, acc);
+                                if (!PRED) umma_tf32(tmem + T_C, dS3 + ko, dP + ko, idA, acc);
                                 umma_tf32(tmem + T_B, dWb + ko, dF + ko, idB, acc);
-                                umma_tf32(tmem + T_D, dW2 + ko, dF + ko, idB, acc);
+                                if (!PRED) umma_tf32(tmem + T_D, dW2 + ko, dF + ko, idB, acc);
                             }
                             umma_commit(&bar_empty[s]);
                             if (kb == nkb - 1) umma_commit(&bar_gram);
@@ -332,7 +343,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                             // this copy has read it
                             float* rp = rbase + (size_t)kb * RP_KB_FLOATS;
                             bulk_s2g(rp, sb, RP_TILE);
-                            if (!red) bulk_s2g(rp + A_TILE / 4, sb + 2 * A_TILE, RP_TILE);
+                            if (!red && !PRED) bulk_s2g(rp + A_TILE / 4, sb + 2 * A_TILE, RP_TILE);
                             bulk_commit_group();
                             bulk_wait_group_read0();
                             mbar_arrive(&bar_empty[s]);
@@ -345,7 +356,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                             const int s = rit % RP_NST;
                             const uint32_t u = rit / RP_NST;
                             if (u > 0) mbar_wait_or_trap(&bar_rp_empty[s], (u - 1) & 1);     // the MMAs that read the stage retired
-                            const bool red = kb * KB >= Nb;
+                            const bool red = PRED || kb * KB >= Nb;
                             unsigned char* dst = ring + (size_t)s * RP_STAGE;
                             const float* src = rbase + (size_t)kb * RP_KB_FLOATS;
                             mbar_expect_tx(&bar_rp_full[s], red ? RP_TILE : 2 * RP_TILE);
@@ -376,7 +387,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                                 const uint64_t ko = (uint64_t)(2 * kk);
                                 const bool acc = (kb | kk) != 0;
                                 umma_tf32(tmem + T_A, dS2 + ko, dP + ko, idA, acc);
-                                umma_tf32(tmem + T_C, dS3 + ko, dP + ko, idA, acc);
+                                if (!PRED) umma_tf32(tmem + T_C, dS3 + ko, dP + ko, idA, acc);
                             }
                             umma_commit(&bar_rp_empty[s]);
                             if (kb == nkb - 1) umma_commit(&bar_gram);
@@ -395,7 +406,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                 G32Worker wa;
                 wa.x = f.x + (size_t)b0 * P; wa.err = f.err + (size_t)b0 * P; wa.mask = f.mask + (size_t)b0 * P;
                 wa.zabs = f.zabs + (size_t)b0 * Nb;
-                wa.Psi = f.Psi; wa.omega = f.omega;
+                wa.Psi = f.Psi; wa.omega = f.omega; wa.mu = f.mu;
                 wa.zero = reinterpret_cast<const uint8_t*>(g.PB + (size_t)nkb * (PB32_KB_BYTES / 4));   // 16 zero bytes after the image
                 wa.P = P; wa.Nb = Nb; wa.nkb = nkb; wa.nr = nr; wa.warp = warp; wa.lane = lane;
                 wa.git0 = git0;
@@ -403,7 +414,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                 wa.bar_full = bar_full; wa.bar_empty = bar_empty;
                 wa.sE = sE + RPW * warp; wa.sNb = sNb + RPW * warp;
                 wa.trace = (kTrace && g.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && lane == 0) ? g.trace + warp * 4 : nullptr;
-                gram32_pass0_worker(wa, pc);
+                gram32_pass0_worker<PRED, PART>(wa, pc);
             }
             named_bar_sync(1, NTHREADS);            // sE / sNb visible; every worker is done with the ring
             // ----------------------------------------------------------- drain the accumulators (warps 0..3: lane = spectrum row)
@@ -417,7 +428,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                 for (int c = 0; c < ncol; c += 16) {
                     float va[16], vc[16];
                     tmem_ld16(ta + T_A + c, va);
-                    tmem_ld16(ta + T_C + c, vc);
+                    if (!PRED) tmem_ld16(ta + T_C + c, vc);
                     tmem_wait_ld();
                     if (row_ok) {
                         float4* da = reinterpret_cast<float4*>(dst + G32_M + pass * SLICE + c);
@@ -425,7 +436,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             da[q] = make_float4(va[4 * q], va[4 * q + 1], va[4 * q + 2], va[4 * q + 3]);
-                            dc[q] = make_float4(vc[4 * q], vc[4 * q + 1], vc[4 * q + 2], vc[4 * q + 3]);
+                            if (!PRED) dc[q] = make_float4(vc[4 * q], vc[4 * q + 1], vc[4 * q + 2], vc[4 * q + 3]);
                         }
                     }
                 }
@@ -433,7 +444,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                     for (int c = 0; c < H32; c += 16) {
                         float vb[16], vd[16];
                         tmem_ld16(ta + T_B + c, vb);
-                        tmem_ld16(ta + T_D + c, vd);
+                        if (!PRED) tmem_ld16(ta + T_D + c, vd);
                         tmem_wait_ld();
                         if (row_ok) {
                             float4* db = reinterpret_cast<float4*>(dst + G32_B + c);
@@ -441,7 +452,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 db[q] = make_float4(vb[4 * q], vb[4 * q + 1], vb[4 * q + 2], vb[4 * q + 3]);
-                                dd[q] = make_float4(vd[4 * q], vd[4 * q + 1], vd[4 * q + 2], vd[4 * q + 3]);
+                                if (!PRED) dd[q] = make_float4(vd[4 * q], vd[4 * q + 1], vd[4 * q + 2], vd[4 * q + 3]);
                             }
                         }
                     }
@@ -469,6 +480,9 @@ constexpr int SOLVE32_SMEM = SOLVE32_WARPS * SOLVE32_WARP_FLOATS * 4;           
 #ifndef QFA_SOLVE32_CTAS
 #define QFA_SOLVE32_CTAS 4
 #endif
+#ifndef QFA_SOLVE32_STAGE
+#define QFA_SOLVE32_STAGE 1
+#endif
 
 __device__ __forceinline__ float solve32_rsqrt(float x) {
     const float y = rsqrtf(x);
@@ -481,9 +495,12 @@ __device__ __forceinline__ double solve32_rsqrt(double x) { return rsqrt(x); }
 // first and multiplying (eps x cond(M), cond(M) up to ~1e6 for high signal-to-noise spectra) would not do in float.
 // TC = scalar type of the Cholesky factorisation itself: float by default (identical parity figures on every test case,
 // including the badly conditioned 96-pixel ones; 7 % faster step), double with QFA_FLAG_SOLVE_FP64.
-template <typename TC>
+// PRED = true (prediction, model.py:176-180): no second Gram; outputs NLL, hmean = a, hcov = M^-1 = L^-T L^-1 and the image
+// rows [L^-1 | a] that k_out32 turns into the continuum and its 1-sigma.
+template <typename TC, bool PRED = false>
 __global__ void __launch_bounds__(SOLVE32_WARPS * 32, QFA_SOLVE32_CTAS)
-k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float* __restrict__ nll, float* __restrict__ hasblue) {
+k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float* __restrict__ nll, float* __restrict__ hasblue,
+          float* __restrict__ hmean = nullptr, float* __restrict__ hcov = nullptr, int Nh = H32, int nparts = 1) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     constexpr int LD = SOLVE32_LD;
@@ -500,13 +517,56 @@ k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float*
         //      lane-serial inner loop); afterwards a[k] (k <= lane) = L[lane][k]
         float logdet;
         {
+            // The scratch row holds the PACKED upper triangles: fetched with coalesced 16-byte loads into shared memory (the
+            // L^-1 area, free until the substitution), then unpacked from there.  Reading element tri32(min(k,lane),
+            // max(k,lane)) straight from global memory (one instruction per k) touched ~17 different 32-byte sectors per
+            // instruction: 35 KB of L2 -> SM sector traffic for 4.5 KB of data, 64 serialised scattered loads per spectrum.
+#if QFA_SOLVE32_STAGE
+            {
+                const float4* s4 = reinterpret_cast<const float4*>(src + G32_M);
+                float4* d4 = reinterpret_cast<float4*>(sLi);
+#pragma unroll
+                for (int q = 0; q < (NP2_32 / 4 + 31) / 32; ++q)
+                    if (q * 32 + lane < NP2_32 / 4) {
+                        float4 v = __ldg(s4 + q * 32 + lane);
+                        if (PRED) {          // 3xTF32 prediction Grams: hi*hi + lo*hi + hi*lo come from three launches (small parts first)
+                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int pp = nparts - 1; pp >= 1; --pp) {
+                                const float4 u = __ldg(s4 + (size_t)pp * B * (G32_STRIDE / 4) + q * 32 + lane);
+                                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                            }
+                            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                        }
+                        d4[q * 32 + lane] = v;
+                    }
+                __syncwarp();
+            }
+#endif
             TC a[H32];
 #pragma unroll
             for (int k = 0; k < H32; ++k) {
                 const int lo = k < lane ? k : lane, hi = k < lane ? lane : k;
+#if QFA_SOLVE32_STAGE
+                a[k] = (TC)sLi[tri32(lo, hi)] + (k == lane ? TC(1) : TC(0));
+#else
                 a[k] = (TC)__ldg(src + G32_M + tri32(lo, hi)) + (k == lane ? TC(1) : TC(0));
+#endif
             }
-            sb[lane] = __ldg(src + G32_B + lane);
+            {
+                float bsum = 0.f;
+                if (PRED) for (int pp = nparts - 1; pp >= 1; --pp) bsum += __ldg(src + (size_t)pp * B * G32_STRIDE + G32_B + lane);
+                sb[lane] = __ldg(src + G32_B + lane) + bsum;
+            }
+#if QFA_SOLVE32_STAGE
+            __syncwarp();                                  // every lane has unpacked M: the staging area takes M2 now
+            if (!PRED) {
+                const float4* s4 = reinterpret_cast<const float4*>(src + G32_M2);
+                float4* d4 = reinterpret_cast<float4*>(sLi);
+#pragma unroll
+                for (int q = 0; q < (NP2_32 / 4 + 31) / 32; ++q)
+                    if (q * 32 + lane < NP2_32 / 4) d4[q * 32 + lane] = __ldg(s4 + q * 32 + lane);
+            }
+#endif
             TC myinv = TC(1), mydiag = TC(1);
 #pragma unroll
             for (int j = 0; j < H32; ++j) {
@@ -535,12 +595,22 @@ k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float*
         }
         // column `lane` of M2 (symmetric): issued here so that the scattered loads fly under the substitution
         float m2c[H32];
+#if QFA_SOLVE32_STAGE
+        __syncwarp();                                      // M2 staged (its loads flew under the factorisation)
+#endif
+        float cv = 0.f;
+        if (!PRED) {
 #pragma unroll
-        for (int k = 0; k < H32; ++k) {
-            const int lo = k < lane ? k : lane, hi = k < lane ? lane : k;
-            m2c[k] = __ldg(src + G32_M2 + tri32(lo, hi));
+            for (int k = 0; k < H32; ++k) {
+                const int lo = k < lane ? k : lane, hi = k < lane ? lane : k;
+#if QFA_SOLVE32_STAGE
+                m2c[k] = sLi[tri32(lo, hi)];
+#else
+                m2c[k] = __ldg(src + G32_M2 + tri32(lo, hi));
+#endif
+            }
+            cv = __ldg(src + G32_B2 + lane);
         }
-        float cv = __ldg(src + G32_B2 + lane);
         __syncwarp();
         // ---- column `lane` of L^-1 in registers (forward substitution, rows of L broadcast from shared memory)
         float x[H32];
@@ -591,6 +661,23 @@ k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float*
         sa[lane] = av;
         dst[sw128_offset(2 * H32, lane) / 4] = tf32_rna(av);
         __syncwarp();
+        if (PRED) {
+            // ---- hmean, hcov = L^-T L^-1: column `lane` = sum_j Linv[j][r] Linv[j][lane]; sA row r = Linv[.][r] (broadcast)
+            if (hmean && lane < Nh) hmean[(size_t)b * Nh + lane] = av;
+            if (hcov) {
+#pragma unroll
+                for (int r = 0; r < H32; ++r) {
+                    float sacc = 0.f;
+#pragma unroll
+                    for (int j4 = (r & ~3); j4 < H32; j4 += 4) {
+                        const float4 lv = *reinterpret_cast<const float4*>(sA + r * LD + j4);   // Linv[j4..j4+3][r] (0 for j < r)
+                        sacc = fmaf(lv.x, x[j4], sacc); sacc = fmaf(lv.y, x[j4 + 1], sacc);
+                        sacc = fmaf(lv.z, x[j4 + 2], sacc); sacc = fmaf(lv.w, x[j4 + 3], sacc);
+                    }
+                    if (r < Nh && lane < Nh) hcov[((size_t)b * Nh + r) * Nh + lane] = sacc;
+                }
+            }
+        } else {
         // ---- c = b2 - M2 a  (M2 symmetric: row `lane` = column `lane`)
 #pragma unroll
         for (int k4 = 0; k4 < H32; k4 += 4) {
@@ -635,10 +722,11 @@ k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float*
             }
             *reinterpret_cast<float4*>(dst + sw128_offset(lane, k4) / 4) = make_float4(kk[0], kk[1], kk[2], kk[3]);
         }
+        }
         if (lane == 0) {
             const double E = (double)__ldg(src + G32_E);
             nll[b] = (float)(0.5 * (E - (double)quad + (double)logdet));                       // model.py:135
-            hasblue[b] = __ldg(src + G32_E + 1);
+            if (!PRED) hasblue[b] = __ldg(src + G32_E + 1);
         }
         __syncwarp();
     }
@@ -923,6 +1011,129 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
             float t = 0.f;
             for (int w = 0; w < 4; ++w) t += sred2[tid * 32 + w];
             g.spart[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3 + tid] = t;
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------
+// k_out32: continuum and 1-sigma on the full grid for 8 < Nh <= 32 (model.py:180), cut from k_tc_grad32: for spectrum b and
+// the CTA's 128-pixel tile   D_b[i, 32..63] = (L_b^-1 f_i)  ->  unc_i = |.|   ,   D_b[i, 64] = f_i^T hmean_b -> cont_i = mu_i + .
+// A = the tile's rows of F, B = the image rows [L^-1 | a] that k_solve32<PRED> wrote; same ring / TMEM double buffering.
+// lane = pixel: every store instruction writes 128 consecutive bytes of one spectrum's row.
+// ---------------------------------------------------------------------------------------
+struct TcOut32Args {
+    Field<float> f;
+    int B;
+    int nsplit;
+    const float* img;      // [B (+2 pad)][G32_IMG/4]
+    float* cont;           // [B][P] or nullptr
+    float* unc;            // [B][P] or nullptr
+};
+
+__global__ void __launch_bounds__(G32_THREADS, 1) k_out32(const TcOut32Args g) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* sm = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar_b[G32_NST], bar_tm_full[2], bar_tm_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int quad = warp & 3, grp = warp >> 2;
+    const Field<float>& f = g.f;
+    const int P = f.P, Nh = f.Nh;
+    const int pt = blockIdx.x;
+    const int nsteps_all = (g.B + G32_SPS - 1) / G32_SPS;
+    const int st0 = (int)((long long)blockIdx.y * nsteps_all / g.nsplit);
+    const int st1 = (int)((long long)(blockIdx.y + 1) * nsteps_all / g.nsplit);
+    const int nst = st1 - st0;
+    if (tid == 0) {
+        for (int s = 0; s < G32_NST; ++s) mbar_init(&bar_b[s], 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&bar_tm_full[s], 1); mbar_init(&bar_tm_empty[s], G32_W); }
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+    const int pi = quad * 32 + lane;
+    const int i = pt * 128 + pi;
+    const bool pix_ok = i < P;
+    if (warp < 4) {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = c4 * 4 + q;
+                v[q] = (pix_ok && k < Nh) ? tf32_rna(__ldg(f.F + (size_t)i * Nh + k)) : 0.0f;
+            }
+            sts_v4(smem_u32(sm) + G32_A_OFF + sw128_offset(pi, c4 * 4), v[0], v[1], v[2], v[3]);
+        }
+    }
+    // the whole ring is zeroed once: image rows 0..31 and 65.. are never copied in the prediction flavour (the copies bring rows
+    // 32..64 only), and an MMA must not read uninitialised shared memory (NaN patterns would not matter -- D columns are
+    // independent -- but stay deterministic)
+    for (int q = tid; q < G32_NST * G32_STAGE / 16; q += G32_THREADS) sts_v4(smem_u32(sm) + G32_B_OFF + q * 16, 0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t sm_sa = smem_u32(sm);
+    const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16);
+    constexpr int ROW0 = H32, NROWS = H32 + 1;          // image rows 32..64: L^-1 and a
+
+    if (warp == G32_W) {
+        if (nst > 0 && elect_one()) {
+            const uint32_t idN = idesc_tf32(128, G32_SPS * G32_ROWS);
+            auto issue_b = [&](int n) {
+                const int s = n % G32_NST;
+                const size_t b0 = (size_t)(st0 + n) * G32_SPS;
+                mbar_expect_tx(&bar_b[s], G32_SPS * NROWS * 128);
+#pragma unroll
+                for (int sp = 0; sp < G32_SPS; ++sp)
+                    bulk_g2s(sm + G32_B_OFF + s * G32_STAGE + sp * G32_IMG + ROW0 * 128, g.img + (b0 + sp) * (G32_IMG / 4) + ROW0 * 32,
+                             NROWS * 128, &bar_b[s]);
+            };
+            for (int n = 0; n < 2 && n < nst; ++n) issue_b(n);
+            const uint64_t dA = desc_sw128_kmajor(sm_sa + G32_A_OFF);
+            for (int n = 0; n < nst; ++n) {
+                const int buf = n & 1, s = n % G32_NST;
+                if (n >= 2) mbar_wait_or_trap(&bar_tm_empty[buf], ((n >> 1) - 1) & 1);
+                mbar_wait_or_trap(&bar_b[s], (n / G32_NST) & 1);
+                fence_after_sync();
+                const uint64_t dB = desc_sw128_kmajor(sm_sa + G32_B_OFF + s * G32_STAGE);
+                const uint32_t dcol = tmem + buf * G32_TBUF;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma_tf32(dcol, dA + (uint64_t)(2 * kk), dB + (uint64_t)(2 * kk), idN, kk > 0);
+                umma_commit(&bar_tm_full[buf]);
+                if (n + 2 < nst) issue_b(n + 2);
+            }
+        }
+        __syncwarp();
+    } else {
+        const float mu = pix_ok ? __ldg(f.mu + i) : 0.f;
+        for (int n = 0; n < nst; ++n) {
+            const int buf = n & 1;
+            const int b = (st0 + n) * G32_SPS + grp;
+            mbar_wait_or_trap(&bar_tm_full[buf], (n >> 1) & 1);
+            fence_after_sync();
+            const uint32_t tcol = ta + buf * G32_TBUF + grp * G32_ROWS;
+            float z[2][16], w8[8];
+            tmem_ld16(tcol + 32, z[0]); tmem_ld16(tcol + 48, z[1]); tmem_ld8(tcol + 64, w8);
+            tmem_wait_ld();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tm_empty[buf]);
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 16; t += 2) {
+                q0 = fmaf(z[0][t], z[0][t], q0); q1 = fmaf(z[0][t + 1], z[0][t + 1], q1);
+                q2 = fmaf(z[1][t], z[1][t], q2); q3 = fmaf(z[1][t + 1], z[1][t + 1], q3);
+            }
+            if (b < g.B && pix_ok) {
+                if (g.cont) st_stream(g.cont + (size_t)b * P + i, mu + w8[0]);                         // model.py:180
+                if (g.unc) st_stream(g.unc + (size_t)b * P + i, sqrtaf((q0 + q1) + (q2 + q3)));
+            }
         }
     }
     fence_before_sync();

@@ -1,6 +1,6 @@
 """GPU scratch: time QFA.accumulate on the Npix 1000 / Nh 32 workload (tensor-core path)."""
 import sys, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from qfa_b200 import QFA, synth
 grid = synth.GRIDS["l32"]
 P, mu = synth.smooth_random_params(grid, 32, seed=1237)

@@ -1,8 +1,8 @@
 """GPU scratch: run the mixed predict path a few times (for ncu)."""
 import sys, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from qfa_b200 import QFA, synth
-k = np.load('/root/repo/tests/golden/kat_sdss.npz')
+k = np.load(__import__('os').path.join(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))), 'tests', 'golden', 'kat_sdss.npz'))
 P = {key: torch.tensor(k["param_" + key], dtype=torch.float32) for key in ("F", "Psi", "omega", "tau0", "beta")}
 P["c0"] = P["beta"].clone(); mu = torch.tensor(k["param_mu"])
 grid = synth.GRIDS["sdss"]
