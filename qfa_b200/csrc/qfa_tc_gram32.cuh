@@ -68,7 +68,19 @@ constexpr int G32_THREADS = (G32_W + 1) * 32;
 constexpr int G32_A_OFF = 0;                          // 16 KB: F rows of the pixel tile
 constexpr int G32_B_OFF = 16384;
 constexpr int G32_RED_OFF = G32_B_OFF;                // epilogue [3 groups][128 pixels][40] floats: over the (then idle) ring
-constexpr int G32_SMEM = G32_B_OFF + G32_NST * G32_STAGE + 1024;
+#ifndef QFA_G32_CPASYNC
+#define QFA_G32_CPASYNC 0
+#endif
+// EXPERIMENT, measured and switched off (-DQFA_G32_CPASYNC=1 builds it): k_tc_grad32 cell prefetch through shared memory
+// (cp.async, 4 bytes per array and thread, G32_CL steps deep) instead of registers.  Motivation: ncu (round 2) puts 15 % of the
+// kernel's stall samples on the branch at the head of the unrolled step loop, long scoreboard -- the 16 register loads in flight
+// share six hardware scoreboards, so waiting for the oldest cell also waits for the newest.  Result on one B200, 65 536 spectra:
+// 865 -> 938 us (the LDGSTS / LDS / wait_group instructions cost more than the stall they remove); issuing the loads of a whole
+// group of four steps at once into a second register set was worse still (1 228 us: 24 bytes of spills).
+constexpr int G32_CL = 8;
+constexpr int G32_CELL_OFF = G32_B_OFF + G32_NST * G32_STAGE;
+constexpr int G32_CELL_BYTES = QFA_G32_CPASYNC ? G32_CL * 4 * (G32_W * 32) * 4 : 0;
+constexpr int G32_SMEM = G32_B_OFF + G32_NST * G32_STAGE + G32_CELL_BYTES + 1024;
 static_assert(3 * 128 * 40 * 4 <= G32_NST * G32_STAGE, "epilogue staging fits the ring");
 constexpr int G32_TBUF = 256;                         // TMEM columns per buffer (3 x 80 used)
 
@@ -157,7 +169,7 @@ __device__ __forceinline__ void kblock_consume32(const PhysConst& pc, const KBuf
 // latency (period 6 200 cycles, 3 600 of them in the load phase).
 struct G32Worker {
     const float* x; const float* err; const float* zabs; const uint8_t* mask;   // row 0 of the tile
-    const float* Psi; const float* omega; const float* mu; const uint8_t* zero;
+    const float* Psi; const float* omega; const uint8_t* zero;
     int P, Nb, nkb, nr, warp, lane;
     uint32_t git0, ring_sa;
     uint64_t* bar_full; uint64_t* bar_empty;
@@ -169,7 +181,9 @@ template <bool PRED, int PART>
 __device__ __noinline__ void gram32_pass0_worker(const G32Worker w, const PhysConst pc) {
     const int P = w.P, Nb = w.Nb, nkb = w.nkb, nr = w.nr, warp = w.warp, lane = w.lane;
     Field<float> f;
-    f.P = P; f.Nb = Nb; f.Psi = w.Psi; f.omega = w.omega; f.mu = w.mu;
+    // prediction flavour: the mean spectrum travels in the (debug-only, otherwise null) trace slot -- one more by-value member
+    // of this struct changed the register allocation of the TRAIN instance (+10 % kernel time, measured)
+    f.P = P; f.Nb = Nb; f.Psi = w.Psi; f.omega = w.omega; f.mu = PRED ? reinterpret_cast<const float*>(w.trace) : nullptr;
     float E[RPW];
     uint32_t nbm = 0u;
 #pragma unroll
@@ -203,7 +217,7 @@ __device__ __noinline__ void gram32_pass0_worker(const G32Worker w, const PhysCo
             const uint32_t u = git / NSTAGE32;
             const int p0 = kb * KB;
             const bool blue = p0 + lane < Nb;
-            long long* tr = (kTrace && w.trace) ? w.trace + (size_t)kb * NPW * 4 : nullptr;
+            long long* tr = (kTrace && !PRED && w.trace) ? w.trace + (size_t)kb * NPW * 4 : nullptr;
             if (tr) tr[0] = clock64();
             if (u > 0) mbar_wait_or_trap(&bar_empty[s], (u - 1) & 1);
             if (tr) tr[1] = clock64();
@@ -406,14 +420,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_gram32(const TcGram32Args g)
                 G32Worker wa;
                 wa.x = f.x + (size_t)b0 * P; wa.err = f.err + (size_t)b0 * P; wa.mask = f.mask + (size_t)b0 * P;
                 wa.zabs = f.zabs + (size_t)b0 * Nb;
-                wa.Psi = f.Psi; wa.omega = f.omega; wa.mu = f.mu;
+                wa.Psi = f.Psi; wa.omega = f.omega;
                 wa.zero = reinterpret_cast<const uint8_t*>(g.PB + (size_t)nkb * (PB32_KB_BYTES / 4));   // 16 zero bytes after the image
                 wa.P = P; wa.Nb = Nb; wa.nkb = nkb; wa.nr = nr; wa.warp = warp; wa.lane = lane;
                 wa.git0 = git0;
                 wa.ring_sa = smem_u32(ring) + (uint32_t)warp * 1024u + (uint32_t)lane * 4u;
                 wa.bar_full = bar_full; wa.bar_empty = bar_empty;
                 wa.sE = sE + RPW * warp; wa.sNb = sNb + RPW * warp;
-                wa.trace = (kTrace && g.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && lane == 0) ? g.trace + warp * 4 : nullptr;
+                wa.trace = PRED ? reinterpret_cast<long long*>(const_cast<float*>(f.mu))
+                                : ((kTrace && g.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && lane == 0) ? g.trace + warp * 4 : nullptr);
                 gram32_pass0_worker<PRED, PART>(wa, pc);
             }
             named_bar_sync(1, NTHREADS);            // sE / sNb visible; every worker is done with the ring
@@ -868,6 +883,48 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
         const float* cz = f.zabs + (size_t)(st0 * G32_SPS + grp) * Nb + iz;
         const size_t cstride = (size_t)G32_SPS * P, zstride = (size_t)G32_SPS * Nb;
         int cleft = pix_ok ? (g.B - grp + G32_SPS - 1) / G32_SPS - st0 : 0;       // steps whose spectrum exists
+#if QFA_G32_CPASYNC
+        const uint8_t* const mask_end = f.mask + (size_t)g.B * P;
+        const uint32_t cell_sa = sm_sa + G32_CELL_OFF + (uint32_t)tid * 4u;          // [slot][x | e | z | mask word][thread]
+        constexpr uint32_t CARR = G32_W * 32 * 4, CSLOT = 4 * CARR;
+        uint32_t wslot = 0, rslot = 0;
+        uint32_t rsh = (uint32_t)((uintptr_t)cm & 3u) * 8u;                              // bit offset of this thread's mask byte in its word
+        const uint32_t rsh_step = (uint32_t)(cstride & 3u) * 8u;
+        auto cp4 = [](uint32_t dst, const void* src) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+        };
+        auto issue_cell = [&]() {
+            const uint32_t dst = cell_sa + wslot * CSLOT;
+            wslot = wslot + 1 == G32_CL ? 0 : wslot + 1;
+            if (cleft > 0) {
+                cp4(dst, cx);
+                cp4(dst + CARR, ce);
+                if (any_blue) cp4(dst + 2 * CARR, cz);
+                const uint8_t* wa = reinterpret_cast<const uint8_t*>((uintptr_t)cm & ~(uintptr_t)3);   // the aligned word holding the byte
+                if (wa + 4 <= mask_end) cp4(dst + 3 * CARR, wa);
+                else asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + 3 * CARR), "r"(ldg_stream_u8(cm) << (((uintptr_t)cm & 3u) * 8u)) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            --cleft; cx += cstride; ce += cstride; cm += cstride; cz += zstride;
+        };
+        int rleft = cleft;                                    // read-side copy of the "spectrum exists" counter
+        auto read_cell = [&](Cell& c) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(G32_CL - 1) : "memory");
+            const uint32_t src = cell_sa + rslot * CSLOT;
+            rslot = rslot + 1 == G32_CL ? 0 : rslot + 1;
+            if (rleft > 0) {
+                unsigned w;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c.x) : "r"(src));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c.e) : "r"(src + CARR));
+                if (any_blue) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c.z) : "r"(src + 2 * CARR)); else c.z = 0.f;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(src + 3 * CARR));
+                c.m = (w >> rsh) & 0xffu;
+            } else { c.m = 0u; c.x = 0.f; c.e = 1.f; c.z = 0.f; }
+            --rleft; rsh = (rsh + rsh_step) & 31u;
+        };
+#pragma unroll 1
+        for (int q = 0; q < G32_CL; ++q) issue_cell();        // empty groups beyond the last step keep the group count uniform
+#else
         auto load_cell = [&](int, Cell& c) {
             if (cleft > 0) {
                 c.m = ldg_stream_u8(cm);
@@ -882,8 +939,15 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
 #pragma unroll
         for (int q = 0; q < G32_CELL_LEAD; ++q)
             if (q < nst) load_cell(q, cc[q]);
+#endif
         int wstage = 0;                                    // ring stage of the next step (n % G32_NST without the division)
+#if QFA_G32_CPASYNC
+        auto do_step = [&](int n) {
+            Cell cb;
+            read_cell(cb);
+#else
         auto do_step = [&](int n, Cell& cb) {
+#endif
             const int buf = n & 1, s = wstage;
             wstage = wstage + 1 == G32_NST ? 0 : wstage + 1;
             const int b = (st0 + n) * G32_SPS + grp;
@@ -962,6 +1026,16 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
                 }
             }
             if (tr) tr[6] = clock64();
+#if QFA_G32_CPASYNC
+            issue_cell();                                     // the cell of step n + G32_CL
+        };
+        for (int n = 0; n < nst; n += G32_CELL_LEAD) {
+#pragma unroll
+            for (int q = 0; q < G32_CELL_LEAD; ++q)
+                if (n + q < nst) do_step(n + q);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#else
             if (n + G32_CELL_LEAD < nst) load_cell(n + G32_CELL_LEAD, cb);
         };
         for (int n = 0; n < nst; n += G32_CELL_LEAD) {
@@ -969,6 +1043,7 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
             for (int q = 0; q < G32_CELL_LEAD; ++q)
                 if (n + q < nst) do_step(n + q, cc[q]);
         }
+#endif
     }
 
     // ---- end of the CTA: fold the three groups, finish gradF, write the per-split partials

@@ -1,7 +1,7 @@
 import csv, sys
 from collections import Counter
 rows=list(csv.reader(open(sys.argv[1])))
-hdr=rows[1]; data=rows[2:]
+hdr=rows[1]; data=[r for r in rows[2:] if len(r)==len(hdr) and r[0]!='Address']
 ix={h:i for i,h in enumerate(hdr)}
 tot_inst=sum(int(r[ix["Instructions Executed"]]) for r in data)
 tot_samp=sum(int(r[ix["# Samples"]]) for r in data)
