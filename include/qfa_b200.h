@@ -49,7 +49,7 @@ extern "C" {
 /* flags */
 #define QFA_FLAG_ZERO_ACC 1     /* qfa_train_accumulate: clear `acc` before accumulating */
 #define QFA_FLAG_FORCE_TENSOR 2 /* QFA_PREC_TF32: use the tcgen05 kernels even for batches smaller than
-                                   the path's cross-over (predict 1280, train 512, train with
+                                   the path's cross-over (predict 1280 / 640 for Nh > 16, train 800, train with
                                    8 < Nh <= 32: 192 spectra; env QFA_TC_MIN_BATCH overrides) */
 #define QFA_FLAG_SOLVE_FP64 4   /* QFA_PREC_TF32, 8 < Nh <= 32: per-spectrum Cholesky in double instead of float (7 % slower
                                    train step; no measurable difference on any parity case, kept for ill-conditioned models) */

@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 PREC_FP64, PREC_FP32, PREC_TF32 = 0, 1, 2
-# "mixed": tensor cores above the path's cross-over batch size (predict 1280, train 512 / 192; env QFA_TC_MIN_BATCH),
+# "mixed": tensor cores above the path's cross-over batch size (predict 1280, train 800 / 192; env QFA_TC_MIN_BATCH),
 # float CUDA cores below; "tf32": always tensor cores
 PRECISIONS = {"fp64": PREC_FP64, "fp32": PREC_FP32, "mixed": PREC_TF32, "tf32": PREC_TF32, "tf32x3": PREC_TF32}
 TAU_LAWS = {"becker": 0, "fg": 1, "kamble": 2, "mock": 3}

@@ -163,7 +163,7 @@ static int tc_min_batch(int path) {
         if (s && v < 0) v = 0;
     }
     if (v >= 0) return v;
-    return path == TC_PATH_PREDICT ? 1280 : (path == TC_PATH_TRAIN ? 512 : (path == TC_PATH_TRAIN32 ? 192 : 640));
+    return path == TC_PATH_PREDICT ? 1280 : (path == TC_PATH_TRAIN ? 800 : (path == TC_PATH_TRAIN32 ? 192 : 640));
 }
 static inline bool tc_use(int Nh, int precision, int B, int flags, int path) {
     return tc_eligible(Nh, precision) && (B >= tc_min_batch(path) || (flags & QFA_FLAG_FORCE_TENSOR));
@@ -382,6 +382,9 @@ static int check_model(const QfaModel* m, int precision) {
 // ---------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------
+#ifndef QFA_SMEM_PER_SM_KB
+#define QFA_SMEM_PER_SM_KB 227      // usable shared memory per SM (228 KB minus 1 KB reserved per CTA is accounted for below)
+#endif
 template <typename T, int HP, int MODE>
 static cudaError_t launch_gram(const GramArgs<T>& a, cudaStream_t st) {
     using C = GramCfg<T, HP, MODE>;
@@ -392,7 +395,7 @@ static cudaError_t launch_gram(const GramArgs<T>& a, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         attr_once.done[current_device()] = true;
     }
-    int per_sm = (int)((size_t)220 * 1024 / (C::smem_bytes + 1024));
+    int per_sm = (int)((size_t)QFA_SMEM_PER_SM_KB * 1024 / (C::smem_bytes + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     int grid = num_sms() * per_sm;
@@ -1018,9 +1021,9 @@ static int gather_prepare(const float* flux, const float* error, const uint8_t* 
     a.perm = reinterpret_cast<const int64_t*>(perm); a.cursor = reinterpret_cast<const int64_t*>(cursor);
     a.B = B; a.Nb = Nb; a.P = Nb + Nr; a.max_series = aux::kNSeries; a.lw = aux_law(tau_law);
     a.zabs_out = zabs_out; a.delta_out = delta_out; a.error_out = error_out; a.mask_out = mask_out;
-    const int gx = (a.P + 255) / 256;
-    int gy = B < 65535 ? B : 65535;
-    aux::k_gather_prepare<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(a); QFA_LAUNCHED();
+    int grid = 8 * num_sms();                       // 8 CTAs of 256 threads per SM, each streaming whole rows
+    if (grid > B) grid = B;
+    aux::k_gather_prepare<<<grid, 256, 0, (cudaStream_t)stream>>>(a); QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }

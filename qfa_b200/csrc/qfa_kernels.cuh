@@ -150,7 +150,14 @@ struct GramCfg {
 };
 
 template <typename T, int HP, int MODE>
-__global__ void __launch_bounds__(256) k_gram_solve(GramArgs<T> g) {
+#ifndef QFA_GRAMSOLVE_MINB
+#define QFA_GRAMSOLVE_MINB 4
+#endif
+// HP <= 8, float: four CTAs per SM (64 registers per thread instead of 80, 4 x 56.8 KB of shared memory = the 227 KB an SM
+// offers, see launch_gram).  Measured on one B200: a batch of 500 spectra -- the reference's default -- fits ONE wave of
+// 592 CTAs instead of 1.13 waves of 444 (captured train step 140 -> 96 us), and the float mode as a whole gains
+// (predict 9.2 -> 12.2, train step 4.5 -> 7.8 M spectra/s).
+__global__ void __launch_bounds__(256, (HP <= 8 && sizeof(T) == 4) ? QFA_GRAMSOLVE_MINB : 1) k_gram_solve(GramArgs<T> g) {
     using C = GramCfg<T, HP, MODE>;
     constexpr int NT = C::NT, PC = C::PC, NBK = C::NBK, NSL = C::NSL, NACC = C::NACC, LD = C::LD;
     constexpr bool TRAIN = C::TRAIN;

@@ -16,7 +16,7 @@ Precision modes (constructor argument `precision`):
           reference is a float32 program, this mode is at least as accurate as what it replaces and its
           results do not depend on the batch size.
   'fp64'  double everywhere: the parity mode (<= 1e-5 against the fp64-promoted reference).
-  'mixed' opt-in speed mode: above a per-path batch size (predict 1280, train step 512 / 192 spectra) the
+  'mixed' opt-in speed mode: above a per-path batch size (predict 1280, train step 800 / 192 spectra) the
           contractions run on the tensor cores with TF32-rounded operands (continuum <= 1e-3); below it the
           'fp32' kernels run.  NOTE: the same model therefore gives slightly different numbers for different
           batch sizes (e.g. the last partial batch of an epoch), and the TF32 error grows with
