@@ -14,10 +14,16 @@ CASES = ("sdss", "l32", "tiny5", "tiny12", "tiny3k", "tiny8m", "tiny16", "tiny1"
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    # the in-tree library is git-ignored: (re)build it when it is missing or older than its sources (nvcc cross-compiles
-    # sm_100a without a GPU; a fresh build takes ~1 minute, an up-to-date one is a no-op)
-    from qfa_b200 import _lib
-    _lib.build()
+
+
+def pytest_collection_finish(session):
+    """The in-tree library is git-ignored: (re)build it when it is missing or older than its sources -- but only when a
+    SELECTED test needs it (the GPU tests; tests/test_capi_symbols.py and the bench contract build it themselves), so
+    that the host-only tests run on a machine without nvcc.  nvcc cross-compiles sm_100a without a GPU; a fresh build takes
+    ~1 minute, an up-to-date one is a no-op."""
+    if any(item.get_closest_marker("gpu") is not None for item in session.items):
+        from qfa_b200 import _lib
+        _lib.build()
 
 
 def load_case(name, tag=None):

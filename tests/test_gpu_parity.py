@@ -136,7 +136,9 @@ def test_tensor_core_path_against_fp64_golden(name, cuda_model_factory):
     loss, grads = m.forward(dev(c["delta"]), dev(c["error"]), dev(c["zabs"]), dev(c["mask"]))
     assert abs(float(loss) - float(np.squeeze(g["loss"]))) <= (1e-3 if real else 1e-2) * npx.mean()
     for k in KEYS:
-        assert relerr(grads[k].cpu().numpy(), g["grad_" + k]) < 5e-2, k       # incl. NaN placement (0/0)
+        # incl. NaN placement (0/0).  Measured: 8.6e-4 (gradF) / 1.2e-4 on the reference's own model, <= 2.2e-2 on the
+        # badly conditioned 96-pixel cases (12 spectra: no averaging of the operand rounding)
+        assert relerr(grads[k].cpu().numpy(), g["grad_" + k]) < (3e-3 if real else 5e-2), k
 
 
 def test_tensor_core_path_ragged_tiles_and_properties():
@@ -705,3 +707,64 @@ def test_tensor_core_nh32_predict_path(cuda_model_factory):
         om = mx.predict_batch(*a)
         same_as_tc = torch.equal(om["cont"], full["cont"])
         assert same_as_tc == (Nh > 16)
+
+
+# ----------------------------------------------------------------------------- ill-conditioned inputs
+def test_high_signal_to_noise_spectra_all_float_modes():
+    """Ill-conditioned inputs: Psi and omega at their clip floor 1e-3 (model.py:237-238), quoted errors 20x
+    smaller than usual (S/N 40-400) -- large weights 1/D -- and a factor matrix with two nearly collinear pairs of columns
+    (with the pretrained F alone cond(I + F^T W F) saturates at ~30 however large the weights): cond(M) ~ 1e4, and every float
+    path loses accuracy in proportion.  The float CUDA-core mode (the default) and
+    the 3xTF32 tensor-core mode must still hold the continuum to 1e-4; single-pass TF32 ('tf32', and 'mixed' above its
+    cross-over) is the opt-in speed mode and its error on such data is measured and bounded here, not hidden."""
+    from qfa_b200 import QFA, synth
+    P, mu = _sdss_pretrained()
+    F2 = P["F"].clone()
+    F2[:, 1] = F2[:, 0] + 0.03 * F2[:, 1]                # two nearly collinear factors: the Gram itself becomes ill-conditioned
+    F2[:, 3] = F2[:, 2] - 0.05 * F2[:, 3]
+    P = dict(P, F=F2, Psi=torch.full_like(P["Psi"], 1e-3), omega=torch.full_like(P["omega"], 1e-3))
+    grid = synth.GRIDS["sdss"]
+    dev0 = torch.device("cuda:0")
+    d = synth.make_spectra(P, mu, grid, 600, seed=21, device=dev0)
+    err = torch.where(d["mask"], d["error"] * 0.05, d["error"])
+    Pn = {k: v.numpy() for k, v in P.items()}
+    a = [d["flux"], err, d["zabs"], d["mask"]]
+    ref = QFA(grid.Nb, grid.Nr, 8, dev0, model_params=Pn, precision="fp64"); ref.mu = mu
+    o0 = ref.predict_batch(*a)
+    cond = torch.linalg.cond(torch.linalg.inv(o0["hcov"])).cpu().numpy()
+    print("cond(M): median %.1e max %.1e" % (np.median(cond), cond.max()))
+    assert np.median(cond) > 1e3, cond
+    res = {}
+    for prec in ("fp32", "tf32x3", "tf32"):
+        m = QFA(grid.Nb, grid.Nr, 8, dev0, model_params=Pn, precision=prec); m.mu = mu
+        o = m.predict_batch(*a)
+        res[prec] = {k: relerr(o[k].cpu().numpy(), o0[k].cpu().numpy()) for k in ("cont", "unc", "hmean", "hcov")}
+        print("high S/N", prec, {k: "%.1e" % v for k, v in res[prec].items()})
+    # measured at cond(M) ~ 9e3: fp32 and 3xTF32 sit on the same float floor (continuum 1e-5, hmean 1e-3, hcov 2e-3 ~ eps x
+    # cond); single-pass TF32 still holds the continuum to 7.5e-4 but hmean / hcov / sigma are 6e-2 / 1.4e-1 / 1.8e-1 off
+    for prec in ("fp32", "tf32x3"):
+        assert res[prec]["cont"] < 1e-4 and res[prec]["hmean"] < 5e-3 and res[prec]["hcov"] < 1e-2, prec
+    assert res["tf32"]["cont"] < 1e-2 and res["tf32"]["hmean"] < 0.3   # degrades with cond(M): the documented price of the opt-in mode
+
+
+def test_data_parallel_sum_on_two_gpus():
+    """N > 1 on hardware (runs where two devices are visible, e.g. `gpurun --gpus 2`): two shards accumulated on two
+    devices, summed, equal the single-device accumulation of the whole batch -- counts exactly, sums to round-off.
+    (The NCCL path itself is asserted inside every multi-GPU bench run: bench.py dp_parity.)"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from qfa_b200 import QFA, synth
+    P, mu = _sdss_pretrained()
+    grid = synth.GRIDS["sdss"]
+    Pn = {k: v.numpy() for k, v in P.items()}
+    d = synth.make_spectra(P, mu, grid, 2400, seed=8, device=torch.device("cuda:0"))
+    keys = ("delta", "error", "zabs", "mask")
+    m0 = QFA(grid.Nb, grid.Nr, 8, torch.device("cuda:0"), model_params=Pn, precision="tf32")
+    m1 = QFA(grid.Nb, grid.Nr, 8, torch.device("cuda:1"), model_params=Pn, precision="tf32")
+    whole = m0.accumulate(*[d[k] for k in keys]).clone()
+    a0 = m0.accumulate(*[d[k][:1200].contiguous() for k in keys]).clone()
+    a1 = m1.accumulate(*[d[k][1200:].to("cuda:1").contiguous() for k in keys]).to("cuda:0")
+    s = a0 + a1
+    n = m0.Nparams
+    assert torch.equal(s[n:n + grid.Npix + 3], whole[n:n + grid.Npix + 3]) and float(s[n + grid.Npix + 4]) == 2400.0
+    assert relerr(s[:n].cpu().numpy(), whole[:n].cpu().numpy()) < 1e-5
