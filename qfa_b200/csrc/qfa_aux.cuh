@@ -151,11 +151,17 @@ __global__ void __launch_bounds__(1024) k_ood_select(const float* nll, int B, fl
     if (tid == 0) { s_n_gt = 0; }
     __syncthreads();
     if (count_out) {
-        for (int b = tid; b < B; b += NT) {
-            const float v = nll[b];
-            if (v > threshold || v != v) {
-                const uint32_t slot = atomicAdd(&s_n_gt, 1u);
-                if (thr_idx && (int)slot < thr_cap) thr_idx[slot] = b;
+        for (int b0 = 0; b0 < B; b0 += NT) {                 // warp-aggregated compaction: one shared atomic per warp and trip
+            const int b = b0 + tid;
+            const float v = b < B ? nll[b] : 0.f;
+            const bool hit = b < B && (v > threshold || v != v);
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                uint32_t base = 0;
+                if ((tid & 31) == (__ffs(m) - 1)) base = atomicAdd(&s_n_gt, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                const uint32_t slot = base + __popc(m & ((1u << (tid & 31)) - 1u));
+                if (hit && thr_idx && (int)slot < thr_cap) thr_idx[slot] = b;
             }
         }
         __syncthreads();
@@ -173,9 +179,18 @@ __global__ void __launch_bounds__(1024) k_ood_select(const float* nll, int B, fl
         __syncthreads();
         const uint32_t prefix = s_prefix;
         const uint32_t pmask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
-        for (int b = tid; b < B; b += NT) {
-            const uint32_t key = f2key(nll[b]);
-            if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        // NLLs of one data set share their leading bits: almost every element hits the SAME bin in the first passes, so the
+        // counts are aggregated per warp before they touch shared memory (one atomic per distinct digit and warp)
+        for (int b0 = 0; b0 < B; b0 += NT) {
+            const int b = b0 + tid;
+            const uint32_t key = b < B ? f2key(nll[b]) : 0u;
+            const bool in = b < B && (key & pmask) == prefix;
+            const uint32_t digit = (key >> shift) & 255u;
+            const uint32_t act = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const uint32_t peers = __match_any_sync(act, digit);
+                if ((tid & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+            }
         }
         __syncthreads();
         if (tid == 0) {
@@ -205,10 +220,26 @@ __global__ void __launch_bounds__(1024) k_ood_select(const float* nll, int B, fl
         }
     }
     __syncthreads();
-    if (tid == 0) {                                 // ties: ascending index order, serial (need_eq is almost always 1)
-        uint32_t got = 0, base = s_n_gt;
-        for (int b = 0; b < B && got < need_eq; ++b)
-            if (f2key(nll[b]) == T) { skey[base + got] = ((uint64_t)T << 32) | (uint32_t)(~(uint32_t)b); ++got; }
+    // ties at the k-th value: the need_eq SMALLEST indices among the elements equal to T.  Rounds of "block-wide minimum index
+    // above the last one taken" (need_eq is almost always 1: one round)
+    __shared__ uint32_t s_min;
+    {
+        uint32_t last = 0xFFFFFFFFu;                // index taken in the previous round (as +1 offset logic below)
+        int lower = 0;                              // candidates must have index >= lower
+        for (uint32_t got = 0; got < need_eq; ++got) {
+            if (tid == 0) s_min = 0xFFFFFFFFu;
+            __syncthreads();
+            uint32_t mine = 0xFFFFFFFFu;
+            for (int b = lower + tid; b < B; b += NT)
+                if (f2key(nll[b]) == T) { mine = (uint32_t)b; break; }          // this thread's smallest candidate (strided order)
+            if (mine != 0xFFFFFFFFu) atomicMin(&s_min, mine);
+            __syncthreads();
+            last = s_min;
+            if (tid == 0) skey[s_n_gt + got] = ((uint64_t)T << 32) | (uint32_t)(~last);
+            lower = (int)last + 1;
+            __syncthreads();
+        }
+        (void)last;
     }
     __syncthreads();
     // ---- bitonic sort (descending) of the k entries, padded with zeros to a power of two

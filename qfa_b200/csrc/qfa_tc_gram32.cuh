@@ -544,13 +544,10 @@ k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float*
                 for (int q = 0; q < (NP2_32 / 4 + 31) / 32; ++q)
                     if (q * 32 + lane < NP2_32 / 4) {
                         float4 v = __ldg(s4 + q * 32 + lane);
-                        if (PRED) {          // 3xTF32 prediction Grams: hi*hi + lo*hi + hi*lo come from three launches (small parts first)
-                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                            for (int pp = nparts - 1; pp >= 1; --pp) {
-                                const float4 u = __ldg(s4 + (size_t)pp * B * (G32_STRIDE / 4) + q * 32 + lane);
-                                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
-                            }
-                            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                        if (PRED && nparts == 3) {   // 3xTF32 prediction Grams: hi*hi + lo*hi + hi*lo from three launches (small parts first)
+                            const float4 u1 = __ldg(s4 + (size_t)1 * B * (G32_STRIDE / 4) + q * 32 + lane);
+                            const float4 u2 = __ldg(s4 + (size_t)2 * B * (G32_STRIDE / 4) + q * 32 + lane);
+                            v.x += u1.x + u2.x; v.y += u1.y + u2.y; v.z += u1.z + u2.z; v.w += u1.w + u2.w;
                         }
                         d4[q * 32 + lane] = v;
                     }
@@ -569,7 +566,8 @@ k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float*
             }
             {
                 float bsum = 0.f;
-                if (PRED) for (int pp = nparts - 1; pp >= 1; --pp) bsum += __ldg(src + (size_t)pp * B * G32_STRIDE + G32_B + lane);
+                if (PRED && nparts == 3)
+                    bsum = __ldg(src + (size_t)1 * B * G32_STRIDE + G32_B + lane) + __ldg(src + (size_t)2 * B * G32_STRIDE + G32_B + lane);
                 sb[lane] = __ldg(src + G32_B + lane) + bsum;
             }
 #if QFA_SOLVE32_STAGE
@@ -1159,14 +1157,15 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_out32(const TcOut32Args g) {
 
     if (warp == G32_W) {
         if (nst > 0 && elect_one()) {
-            const uint32_t idN = idesc_tf32(128, G32_SPS * G32_ROWS);
+            constexpr int OROWS = 48;                                    // ring rows per spectrum: L^-1 (32), a (1), zero padding (15)
+            const uint32_t idN = idesc_tf32(128, G32_SPS * OROWS);       // the three spectra of a step are ONE 144-row B operand
             auto issue_b = [&](int n) {
                 const int s = n % G32_NST;
                 const size_t b0 = (size_t)(st0 + n) * G32_SPS;
                 mbar_expect_tx(&bar_b[s], G32_SPS * NROWS * 128);
 #pragma unroll
-                for (int sp = 0; sp < G32_SPS; ++sp)
-                    bulk_g2s(sm + G32_B_OFF + s * G32_STAGE + sp * G32_IMG + ROW0 * 128, g.img + (b0 + sp) * (G32_IMG / 4) + ROW0 * 32,
+                for (int sp = 0; sp < G32_SPS; ++sp)                     // image rows 32..64 -> rows 0..32 of the spectrum's compact block
+                    bulk_g2s(sm + G32_B_OFF + s * G32_STAGE + sp * OROWS * 128, g.img + (b0 + sp) * (G32_IMG / 4) + ROW0 * 32,
                              NROWS * 128, &bar_b[s]);
             };
             for (int n = 0; n < 2 && n < nst; ++n) issue_b(n);
@@ -1176,6 +1175,8 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_out32(const TcOut32Args g) {
                 if (n >= 2) mbar_wait_or_trap(&bar_tm_empty[buf], ((n >> 1) - 1) & 1);
                 mbar_wait_or_trap(&bar_b[s], (n / G32_NST) & 1);
                 fence_after_sync();
+                // (the N = 240 MMA over whole 80-row images that k_tc_grad32 issues made this kernel tensor-bound: 617 us; one
+                //  N = 48 MMA per spectrum made it issue-bound in the control thread: 749 us)
                 const uint64_t dB = desc_sw128_kmajor(sm_sa + G32_B_OFF + s * G32_STAGE);
                 const uint32_t dcol = tmem + buf * G32_TBUF;
 #pragma unroll
@@ -1192,9 +1193,9 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_out32(const TcOut32Args g) {
             const int b = (st0 + n) * G32_SPS + grp;
             mbar_wait_or_trap(&bar_tm_full[buf], (n >> 1) & 1);
             fence_after_sync();
-            const uint32_t tcol = ta + buf * G32_TBUF + grp * G32_ROWS;
+            const uint32_t tcol = ta + buf * G32_TBUF + grp * 48;         // this spectrum's 48 columns: L^-1 f (32) | f.a (1) | 0
             float z[2][16], w8[8];
-            tmem_ld16(tcol + 32, z[0]); tmem_ld16(tcol + 48, z[1]); tmem_ld8(tcol + 64, w8);
+            tmem_ld16(tcol, z[0]); tmem_ld16(tcol + 16, z[1]); tmem_ld8(tcol + 32, w8);
             tmem_wait_ld();
             fence_before_sync();
             __syncwarp();
