@@ -560,7 +560,7 @@ static int train_accumulate_tc32(const QfaModel* m, const float* delta, const fl
     CK(cudaGetLastError());
     TcGrad32Args gr;
     gr.f = f; gr.B = B; gr.nsplit = pl.nsplit; gr.img = small; gr.part = part; gr.spart = spart; gr.trace = g_trace_grad;
-    k_tc_grad32<<<dim3(pl.npix_tiles, pl.nsplit), G32_THREADS, G32_SMEM, st>>>(gr); QFA_LAUNCHED();
+    k_tc_grad32<<<dim3(pl.npix_tiles, pl.nsplit), QFA_G32_CHAIN ? G32_THREADS_CHAIN : G32_THREADS, G32_SMEM, st>>>(gr); QFA_LAUNCHED();
     CK(cudaGetLastError());
     ReduceArgs<float> ra;
     ra.part = part; ra.spart = spart; ra.nll = nll; ra.hasblue = hasblue; ra.scal = f.scal;

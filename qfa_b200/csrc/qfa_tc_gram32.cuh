@@ -64,10 +64,20 @@ constexpr int G32_SPS = 3;                            // spectra per step
 constexpr int G32_STAGE = G32_SPS * G32_IMG;          // 30 720 B
 constexpr int G32_NST = 5;                            // image ring stages (see k_tc_grad32: copy of step n+2 overwrites step n-3)
 constexpr int G32_W = 12;                             // worker warps
-constexpr int G32_THREADS = (G32_W + 1) * 32;
+constexpr int G32_THREADS = (G32_W + 1) * 32;            // k_out32, and k_tc_grad32 without the chained MMA
+constexpr int G32_THREADS_CHAIN = (G32_W + 2) * 32;      // chained form: a second control warp issues the TMEM-A MMAs
 constexpr int G32_A_OFF = 0;                          // 16 KB: F rows of the pixel tile
 constexpr int G32_B_OFF = 16384;
 constexpr int G32_RED_OFF = G32_B_OFF;                // epilogue [3 groups][128 pixels][40] floats: over the (then idle) ring
+// EXPERIMENT, measured and switched off (-DQFA_G32_CHAIN=1 builds it; parity tests pass with it): k_solve32 stops at
+// W = L^-1 M2 and k_tc_grad32 finishes f^T K = (L^-1 f)^T W with a SECOND, chained MMA whose A operand is the first MMA's
+// result read straight from tensor memory (tcgen05.mma with A in TMEM), so that the 32 x 32 x 32 triangular product
+// K = L^-T W leaves the CUDA cores.  Result on one B200, 65 536 spectra: k_solve32 575 -> 495 us, but k_tc_grad32 865 ->
+// 1 083 us (1 113 with the chained MMAs on a control warp of their own): the twelve N = 32, K = 8 TMEM-A MMAs per step cost
+// ~100 cycles each in the tensor pipe, which makes the kernel tensor-bound at ~1 750 cycles per step.  Net 2.16 -> 2.30 ms.
+#ifndef QFA_G32_CHAIN
+#define QFA_G32_CHAIN 0
+#endif
 #ifndef QFA_G32_CPASYNC
 #define QFA_G32_CPASYNC 0
 #endif
@@ -714,6 +724,14 @@ k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float*
             }
             wv[r] = sacc;
         }
+#if QFA_G32_CHAIN
+        // ---- image rows 0..31 = W^T: row `lane`, column r = W[r][lane] (this lane's registers).  k_tc_grad32 forms
+        //      (f^T K)_n = sum_r (L^-1 f)_r W[r][n] with a chained MMA (A = L^-1 f from tensor memory)
+#pragma unroll
+        for (int r4 = 0; r4 < H32; r4 += 4)
+            *reinterpret_cast<float4*>(dst + sw128_offset(lane, r4) / 4) =
+                make_float4(tf32_rna(wv[r4]), tf32_rna(wv[r4 + 1]), tf32_rna(wv[r4 + 2]), tf32_rna(wv[r4 + 3]));
+#else
         // ---- K = L^-T W, column `lane`:  K[k] = sum_{r >= k} Linv[r][k] W[r]   (rows of L^-T broadcast).  Image rows 0..31:
         //      B[n][k] = K[k][n] -> this lane owns image row `lane`, four consecutive k per 16-byte store
 #pragma unroll
@@ -735,6 +753,7 @@ k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float*
             }
             *reinterpret_cast<float4*>(dst + sw128_offset(lane, k4) / 4) = make_float4(kk[0], kk[1], kk[2], kk[3]);
         }
+#endif
         }
         if (lane == 0) {
             const double E = (double)__ldg(src + G32_E);
@@ -767,12 +786,18 @@ struct TcGrad32Args {
     float* spart;          // [nsplit][npix_tiles][3]
 };
 
-__global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args g) {
+__global__ void __launch_bounds__(QFA_G32_CHAIN ? G32_THREADS_CHAIN : G32_THREADS, 1) k_tc_grad32(const TcGrad32Args g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* sm = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t bar_b[G32_NST], bar_tm_full[2], bar_tm_empty[2];
+    __shared__ uint64_t bar_b[G32_NST], bar_tm_full[2], bar_tm_empty[2], bar_m1[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float sred2[3 * 32];
+#if QFA_G32_CHAIN
+    // ring stage: [3 compact blocks of 48 rows: L^-1 (32) | a | c | zero padding] [3 blocks of 32 rows: W^T];  TMEM buffer:
+    // [3 x 48 columns: L^-1 f (32) | f.a | f.c | -] [3 x 32 columns: f^T K]
+    constexpr int CROWS = 48, CBLK = CROWS * 128, WOFF = G32_SPS * CBLK, WBLK = H32 * 128, CLIVE = (H32 + 2) * 128;
+    static_assert(WOFF + G32_SPS * WBLK <= G32_STAGE, "chained stage layout fits the ring stage");
+#endif
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -788,7 +813,7 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
 
     if (tid == 0) {
         for (int s = 0; s < G32_NST; ++s) mbar_init(&bar_b[s], 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&bar_tm_full[s], 1); mbar_init(&bar_tm_empty[s], G32_W); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bar_tm_full[s], 1); mbar_init(&bar_tm_empty[s], G32_W); mbar_init(&bar_m1[s], 1); }
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc<512>(&tmem_base_s);
@@ -808,11 +833,16 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
             sts_v4(smem_u32(sm) + G32_A_OFF + sw128_offset(pi, c4 * 4), v[0], v[1], v[2], v[3]);
         }
     }
+#if QFA_G32_CHAIN
+    // the padding rows of the compact blocks are zero and stay zero (the bulk copies only bring the live rows): zero the ring once
+    for (int q = tid; q < G32_NST * G32_STAGE / 16; q += (int)blockDim.x) sts_v4(smem_u32(sm) + G32_B_OFF + q * 16, 0.f, 0.f, 0.f, 0.f);
+#else
     // rows 66..79 of every ring image are zero and stay zero: the bulk copies only bring the 66 live rows
     for (int q = tid; q < G32_NST * G32_SPS * ((G32_IMG - G32_LIVE) / 16); q += G32_THREADS) {
         const int im = q / ((G32_IMG - G32_LIVE) / 16), o = q % ((G32_IMG - G32_LIVE) / 16);
         sts_v4(smem_u32(sm) + G32_B_OFF + im * G32_IMG + G32_LIVE + o * 16, 0.f, 0.f, 0.f, 0.f);
     }
+#endif
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -829,6 +859,38 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
     if (warp == G32_W) {
         // =============================================================== CONTROL warp
         if (nst > 0 && elect_one()) {
+#if QFA_G32_CHAIN
+            const uint32_t idN1 = idesc_tf32(128, G32_SPS * CROWS), id32 = idesc_tf32(128, H32);
+            auto issue_b = [&](int n) {           // step n: image rows 32..65 -> compact blocks, rows 0..31 (W^T) -> W blocks
+                const int s = n % G32_NST;
+                const size_t b0 = (size_t)(st0 + n) * G32_SPS;
+                unsigned char* st = sm + G32_B_OFF + s * G32_STAGE;
+                mbar_expect_tx(&bar_b[s], G32_SPS * (CLIVE + WBLK));
+#pragma unroll
+                for (int sp = 0; sp < G32_SPS; ++sp) {
+                    const float* im = g.img + (b0 + sp) * (G32_IMG / 4);
+                    bulk_g2s(st + sp * CBLK, im + H32 * 32, CLIVE, &bar_b[s]);
+                    bulk_g2s(st + WOFF + sp * WBLK, im, WBLK, &bar_b[s]);
+                }
+            };
+            for (int n = 0; n < 2 && n < nst; ++n) issue_b(n);
+            const uint64_t dA = desc_sw128_kmajor(sm_sa + G32_A_OFF);
+            for (int n = 0; n < nst; ++n) {
+                const int buf = n & 1, s = n % G32_NST;
+                if (n >= 2) mbar_wait_or_trap(&bar_tm_empty[buf], ((n >> 1) - 1) & 1);
+                mbar_wait_or_trap(&bar_b[s], (n / G32_NST) & 1);
+                fence_after_sync();
+                {
+                    const uint64_t dB = desc_sw128_kmajor(sm_sa + G32_B_OFF + s * G32_STAGE);
+                    const uint32_t dcol = tmem + buf * G32_TBUF;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) umma_tf32(dcol, dA + (uint64_t)(2 * kk), dB + (uint64_t)(2 * kk), idN1, kk > 0);
+                }
+                umma_commit(&bar_m1[buf]);
+                if (n + 2 < nst) issue_b(n + 2);
+            }
+        }
+#else
             const uint32_t idN = idesc_tf32(128, G32_SPS * G32_ROWS);     // the 3 images of a stage are ONE 240-row B operand
             auto issue_b = [&](int n) {           // images of step n -> ring stage n % 4
                 const int s = n % G32_NST;              // (single thread, off the critical chain)
@@ -861,7 +923,33 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
                 if (tr) tr[3] = clock64();
             }
         }
+#endif
         __syncwarp();
+#if QFA_G32_CHAIN
+    } else if (warp == G32_W + 1) {
+        // =============================================================== second CONTROL warp: the chained MMAs
+        // (f^T K_b)[i, 0..31] = sum_r z[i, r] W_b[r][.] with A = z = the first MMA's result, read from tensor memory.  A warp of its
+        // own: 12 more MMA issues per step on the first control thread made that thread the bottleneck (1 083 us).
+        if (nst > 0 && elect_one()) {
+            const uint32_t id32 = idesc_tf32(128, H32);
+            for (int n = 0; n < nst; ++n) {
+                const int buf = n & 1, s = n % G32_NST;
+                mbar_wait_or_trap(&bar_m1[buf], (n >> 1) & 1);
+                fence_after_sync();
+                const uint32_t dcol = tmem + buf * G32_TBUF;
+                const uint32_t wb = sm_sa + G32_B_OFF + s * G32_STAGE + WOFF;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                    for (int sp = 0; sp < G32_SPS; ++sp)
+                        umma_tf32_ts(dcol + G32_SPS * CROWS + sp * H32, dcol + sp * CROWS + 8 * kk,
+                                     desc_sw128_kmajor(wb + sp * WBLK) + (uint64_t)(2 * kk), id32, kk > 0);
+                }
+                umma_commit(&bar_tm_full[buf]);
+            }
+        }
+        __syncwarp();
+#endif
     } else {
         // =============================================================== WORKER warps
         const int ic = pix_ok ? i : P - 1;
@@ -956,12 +1044,17 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
             mbar_wait_or_trap(&bar_tm_full[buf], (n >> 1) & 1);
             fence_after_sync();
             if (tr) tr[5] = clock64();
-            const uint32_t tcol = ta + buf * G32_TBUF + grp * G32_ROWS;
             // The TMEM buffer is handed back as soon as its 65 columns are in registers, BEFORE the math: the control warp then
             // runs a full step ahead and the workers never wait for an accumulator.  (The ring stage is still read below -- c,
             // image row 65 -- which is why the ring has 5 stages: the copy for step n+2 goes to the stage of step n-3.)
             float z[2][16], y[2][16], w8[8];
+#if QFA_G32_CHAIN
+            const uint32_t tz = ta + buf * G32_TBUF + grp * CROWS, tcol = ta + buf * G32_TBUF + G32_SPS * CROWS + grp * H32;
+            tmem_ld16(tz, z[0]); tmem_ld16(tz + 16, z[1]); tmem_ld8(tz + 32, w8);
+#else
+            const uint32_t tcol = ta + buf * G32_TBUF + grp * G32_ROWS;
             tmem_ld16(tcol + 32, z[0]); tmem_ld16(tcol + 48, z[1]); tmem_ld8(tcol + 64, w8);
+#endif
             tmem_wait_ld();
             float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
@@ -1009,13 +1102,19 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_tc_grad32(const TcGrad32Args
                     sc2 = fmaf(-t, tau0 * powb * (L2 * kLn2), sc2);                     // model.py:143
                 }
                 // gradF: - s2 (f^T K)_k - (A u) c_k ; c_b = image row 65 (shared memory, broadcast reads)
+#if QFA_G32_CHAIN
+                const uint32_t crow = sm_sa + G32_B_OFF + (uint32_t)s * G32_STAGE + (uint32_t)grp * CBLK;
+                constexpr int CROW_IDX = H32 + 1;                         // compact block row 33 = c
+#else
                 const uint32_t crow = sm_sa + G32_B_OFF + (uint32_t)s * G32_STAGE + (uint32_t)grp * G32_IMG;
+                constexpr int CROW_IDX = 2 * H32 + 1;                     // image row 65 = c
+#endif
                 const float ns2 = -s2, nAu = -Au;
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
                     float cx, cy, cz, cw;
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cx), "=f"(cy), "=f"(cz), "=f"(cw)
-                                 : "r"(crow + sw128_offset(65, 4 * c4)));
+                                 : "r"(crow + sw128_offset(CROW_IDX, 4 * c4)));
                     const int k = 4 * c4;
                     gF[k] = fmaf(ns2, y[k >> 4][k & 15], fmaf(nAu, cx, gF[k]));
                     gF[k + 1] = fmaf(ns2, y[k >> 4][(k & 15) + 1], fmaf(nAu, cy, gF[k + 1]));
@@ -1186,7 +1285,7 @@ __global__ void __launch_bounds__(G32_THREADS, 1) k_out32(const TcOut32Args g) {
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp < G32_W) {
         const float mu = pix_ok ? __ldg(f.mu + i) : 0.f;
         for (int n = 0; n < nst; ++n) {
             const int buf = n & 1;
