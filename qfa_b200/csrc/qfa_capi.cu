@@ -14,6 +14,7 @@
 #include "qfa_tc_gram.cuh"
 #include "qfa_tc_grad.cuh"
 #include "qfa_tc_gram32.cuh"
+#include "qfa_tc_gram32c.cuh"
 #include "qfa_tc_gram_x3.cuh"
 
 using namespace qfa;
@@ -546,16 +547,53 @@ static int train_accumulate_tc32(const QfaModel* m, const float* delta, const fl
         attr_once.done[current_device()] = true;
     }
     Field<float> f = make_field<float>(m, delta, error, zabs, mask);
+    // Gram kernel: the three-pass form.  QFA_GRAM32_CLUSTER=1 selects the 4-CTA cluster form instead (one generation pass, columns
+    // split over the cluster, operand tiles broadcast through distributed shared memory: qfa_tc_gram32c.cuh) -- same results,
+    // MEASURED SLOWER (1 449 vs 711 us on 65 536 spectra, see the header there), kept as a tested experiment.
+    int use_cluster = 0, nclusters = 0;
+    {
+        const char* e = getenv("QFA_GRAM32_CLUSTER");       // read per call: the parity test switches it inside one process
+        if (e && atoi(e)) {
+            static PerDeviceOnce once;
+            static int maxc[kMaxDevices] = {0};
+            if (!once.done[current_device()]) {
+                CK(cudaFuncSetAttribute(k_tc_gram32c, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM));
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(CL_NC * (num_sms() / CL_NC)); cfg.blockDim = dim3(tcg::NTHREADS); cfg.dynamicSmemBytes = CL_SMEM;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL_NC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                int n = 0;
+                if (cudaOccupancyMaxActiveClusters(&n, k_tc_gram32c, &cfg) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+                maxc[current_device()] = n;
+                once.done[current_device()] = true;
+            }
+            nclusters = maxc[current_device()];
+            if (nclusters > pl.ntiles) nclusters = pl.ntiles;
+            use_cluster = nclusters > 0;
+        }
+    }
+    if (use_cluster) {
+        TcGram32cArgs c;
+        c.f = f; c.B = B; c.ts = pl.ts; c.ntiles = pl.ntiles; c.nkb = pl.nkb; c.nclusters = nclusters; c.PB = PB; c.gram = gram;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(CL_NC * nclusters); cfg.blockDim = dim3(tcg::NTHREADS); cfg.dynamicSmemBytes = CL_SMEM; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL_NC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, k_tc_gram32c, c)); QFA_LAUNCHED();
+    } else {
     TcGram32Args a;
     a.f = f; a.B = B; a.ts = pl.ts; a.ntiles = pl.ntiles; a.nkb = pl.nkb; a.PB = PB; a.gram = gram; a.trace = g_trace;
     a.replay = reinterpret_cast<float*>(ws + pl.off_replay);
     int grid = pl.ntiles < num_sms() ? pl.ntiles : num_sms();
     k_tc_gram32<false><<<grid, tcg::NTHREADS, SMEM32_BYTES, st>>>(a); QFA_LAUNCHED();
     CK(cudaGetLastError());
+    }
     int sblocks = (B + SOLVE32_WARPS - 1) / SOLVE32_WARPS;
     if (sblocks > QFA_SOLVE32_CTAS * num_sms()) sblocks = QFA_SOLVE32_CTAS * num_sms();
-    if (flags & QFA_FLAG_SOLVE_FP64) k_solve32<double><<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, small, nll, hasblue);
-    else k_solve32<float><<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, small, nll, hasblue);
+    if (flags & QFA_FLAG_SOLVE_FP64) k_solve32<double><<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, small, nll, hasblue, nullptr, nullptr, H32, 1, use_cluster);
+    else k_solve32<float><<<sblocks, SOLVE32_WARPS * 32, SOLVE32_SMEM, st>>>(gram, B, small, nll, hasblue, nullptr, nullptr, H32, 1, use_cluster);
     QFA_LAUNCHED();
     CK(cudaGetLastError());
     TcGrad32Args gr;

@@ -47,7 +47,7 @@ static_assert(RP_NST * RP_STAGE <= NSTAGE32 * STAGE32_BYTES, "replay stages live
 constexpr int T_A = 0, T_C = SLICE, T_B = 2 * SLICE, T_D = 2 * SLICE + H32;
 // scratch row per spectrum (floats): [M - I packed (528) | M2 packed (528) | b (32) | b2 (32) | E | n_blue>0 | pad]
 constexpr int G32_M = 0, G32_M2 = NP2_32, G32_B = 2 * NP2_32, G32_B2 = 2 * NP2_32 + H32, G32_E = 2 * NP2_32 + 2 * H32;
-constexpr int G32_STRIDE = 1124;
+constexpr int G32_STRIDE = 1128;                      // (+ 8: the four partial E / has-blue values of the cluster kernel, qfa_tc_gram32c.cuh)
 
 // ---- k_tc_grad32 / k_solve32 image geometry
 constexpr int G32_ROWS = 80;                          // image rows per spectrum (UMMA N)
@@ -525,7 +525,8 @@ __device__ __forceinline__ double solve32_rsqrt(double x) { return rsqrt(x); }
 template <typename TC, bool PRED = false>
 __global__ void __launch_bounds__(SOLVE32_WARPS * 32, QFA_SOLVE32_CTAS)
 k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float* __restrict__ nll, float* __restrict__ hasblue,
-          float* __restrict__ hmean = nullptr, float* __restrict__ hcov = nullptr, int Nh = H32, int nparts = 1) {
+          float* __restrict__ hmean = nullptr, float* __restrict__ hcov = nullptr, int Nh = H32, int nparts = 1,
+          int diff = 0) {      // diff = 1: scratch rows of k_tc_gram32c (M2, b2 stored as differences; four partial E / has-blue values)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     constexpr int LD = SOLVE32_LD;
@@ -584,10 +585,18 @@ k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float*
             __syncwarp();                                  // every lane has unpacked M: the staging area takes M2 now
             if (!PRED) {
                 const float4* s4 = reinterpret_cast<const float4*>(src + G32_M2);
+                const float4* g4 = reinterpret_cast<const float4*>(src + G32_M);
                 float4* d4 = reinterpret_cast<float4*>(sLi);
 #pragma unroll
                 for (int q = 0; q < (NP2_32 / 4 + 31) / 32; ++q)
-                    if (q * 32 + lane < NP2_32 / 4) d4[q * 32 + lane] = __ldg(s4 + q * 32 + lane);
+                    if (q * 32 + lane < NP2_32 / 4) {
+                        float4 v = __ldg(s4 + q * 32 + lane);
+                        if (diff) {                               // M2 = (M - I) - Md
+                            const float4 m = __ldg(g4 + q * 32 + lane);
+                            v = make_float4(m.x - v.x, m.y - v.y, m.z - v.z, m.w - v.w);
+                        }
+                        d4[q * 32 + lane] = v;
+                    }
             }
 #endif
             TC myinv = TC(1), mydiag = TC(1);
@@ -633,6 +642,7 @@ k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float*
 #endif
             }
             cv = __ldg(src + G32_B2 + lane);
+            if (diff) cv = __ldg(src + G32_B + lane) - cv;       // b2 = b - b2d
         }
         __syncwarp();
         // ---- column `lane` of L^-1 in registers (forward substitution, rows of L broadcast from shared memory)
@@ -756,9 +766,14 @@ k_solve32(const float* __restrict__ gram, int B, float* __restrict__ img, float*
 #endif
         }
         if (lane == 0) {
-            const double E = (double)__ldg(src + G32_E);
+            double E = (double)__ldg(src + G32_E);
+            float hb = PRED ? 0.f : __ldg(src + G32_E + 1);
+            if (diff) {                                           // four partial sums, one per CTA of the cluster
+                E = ((double)__ldg(src + G32_E) + (double)__ldg(src + G32_E + 1)) + ((double)__ldg(src + G32_E + 2) + (double)__ldg(src + G32_E + 3));
+                hb = (__ldg(src + G32_E + 4) + __ldg(src + G32_E + 5) + __ldg(src + G32_E + 6) + __ldg(src + G32_E + 7)) > 0.f ? 1.0f : 0.0f;
+            }
             nll[b] = (float)(0.5 * (E - (double)quad + (double)logdet));                       // model.py:135
-            if (!PRED) hasblue[b] = __ldg(src + G32_E + 1);
+            if (!PRED) hasblue[b] = hb;
         }
         __syncwarp();
     }

@@ -546,6 +546,36 @@ def test_tensor_core_nh32_ragged_batches():
             assert torch.equal(tc.accumulate(*a), acc1), B
 
 
+@pytest.mark.gpu
+def test_tensor_core_nh32_cluster_gram_experiment(monkeypatch):
+    """k_tc_gram32c (qfa_tc_gram32c.cuh): the Nh 32 Grams on a 4-CTA thread-block cluster -- columns split over the cluster,
+    operand tiles broadcast through distributed shared memory, M2 accumulated as the difference M - Md.  Measured slower than
+    the three-pass kernel and therefore only selected by QFA_GRAM32_CLUSTER=1; its results must agree with the default path
+    (same TF32 operands; M2 / b2 / E are summed in a different order), on full, partial and sub-tile batches."""
+    from qfa_b200 import QFA, synth
+    grid = synth.GRIDS["l32"]
+    P, mu = synth.smooth_random_params(grid, 32, seed=78)
+    Pn = {k: v.numpy() for k, v in P.items()}
+    dev0 = torch.device("cuda:0")
+    tc = QFA(grid.Nb, grid.Nr, 32, dev0, model_params=Pn, precision="tf32")
+    dall = synth.make_spectra(P, mu, grid, 2500, seed=6, device=dev0, mask_iid=0.15, run_len=(40, 160))
+    for B in (5, 121, 2500):
+        a = [dall[k][:B].contiguous() for k in ("delta", "error", "zabs", "mask")]
+        monkeypatch.setenv("QFA_GRAM32_CLUSTER", "0")
+        n0 = torch.empty(B, device="cuda"); tc.accumulate(*a, nll_out=n0); l0, g0 = tc.forward(*a)
+        monkeypatch.setenv("QFA_GRAM32_CLUSTER", "1")
+        n1 = torch.empty(B, device="cuda"); tc.accumulate(*a, nll_out=n1); l1, g1 = tc.forward(*a)
+        monkeypatch.setenv("QFA_GRAM32_CLUSTER", "0")
+        npx = np.maximum(1, a[3].sum(1).cpu().numpy())
+        assert torch.isfinite(n1).all(), B
+        assert (np.abs((n1 - n0).cpu().numpy()) / npx).max() <= 2e-3, B
+        assert abs(float(l1) - float(l0)) <= 1e-3 * npx.mean(), B
+        for k in KEYS:
+            x, y = g1[k].cpu().numpy(), g0[k].cpu().numpy()
+            assert np.array_equal(np.isnan(x), np.isnan(y)), (B, k)
+            assert relerr(x, y) < 2e-2, (B, k)
+
+
 # ----------------------------------------------------------------------------- device dataloader feeding QFA.train
 def test_device_dataloader_on_gpu_and_train(tmp_path):
     """DeviceDataloader on the GPU (delta through qfa_prepare_batch) == the same loader on the CPU (torch restatement of
