@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--spectra", type=int, default=0, help="spectra per GPU per step (0 = workload default)")
     ap.add_argument("--also", default="default", help="comma list of secondary workloads, 'default' or 'none'")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements")
+    ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
+                    help="N > 1 train steps: the library's one-shot peer-memory all-reduce (default) or ncclAllReduce")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -387,7 +389,7 @@ def measure_workload(name, args, rank, world, peaks, want_e2e, want_cpu, nspec_o
     m = QFA(grid.Nb, grid.Nr, Nh, dev, model_params=Pn, precision=precision)
     m.mu = mu
     if world > 1:
-        m.enable_data_parallel()
+        m.enable_data_parallel(peer_allreduce=args.allreduce == "peer")
     kw = dict(mask_iid=0.15, run_len=(40, 160)) if grid_name == "l32" else {}
     ood = 0.01 if kind == "score" else 0.0
     L = _lib.lib()
@@ -483,7 +485,8 @@ def measure_workload(name, args, rank, world, peaks, want_e2e, want_cpu, nspec_o
                 "frac": tf / peaks["tf32_tflops"], "traffic": traffic, "traffic_source": tsrc,
                 "kernel": kernel_names(kind, Nh, precision), "flops_per_spectrum": flops, "peak_source": peaks["tf32_source"]}
     res.update(value=value, ms_per_step=ms / steps, clocks=clocks, gpu_launches=launches, gpu_launches_how=launch_note,
-               roofline=roof, config=workload_config(name, nspec, args.precision, world),
+               roofline=roof, config=dict(workload_config(name, nspec, args.precision, world),
+                                          **({"allreduce": m.allreduce_kind} if world > 1 and kind in ("train", "graph_train") else {})),
                dtype={"fp64": "f64", "fp32": "f32"}.get(precision, "tf32"))
     if "ood" in res:
         res["ood"] = {"top_k": 256, "top_nll_max": float(res["ood"]["top_val"][0]), "top_nll_min": float(res["ood"]["top_val"][-1])}
@@ -544,8 +547,12 @@ def dp_parity_check(rank, world):
     B = 1536
     d = synth.make_spectra(P, mu, grid, B, seed=777 + rank, device=dev)
     ins = [d["delta"], d["error"], d["zabs"], d["mask"].view(torch.uint8)]
-    acc = m.accumulate(*ins, zero=True).clone()
-    dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    loc = m.accumulate(*ins, zero=True).clone()
+    acc = loc.clone()
+    m._allreduce(acc)                                  # the exchange the train step really uses (peer one-shot kernel, or NCCL)
+    nccl = loc.clone()
+    dist.all_reduce(nccl, op=dist.ReduceOp.SUM)
+    vs_nccl = float((acc - nccl).abs().max() / nccl.abs().max())
     gathered = [torch.empty_like(acc) for _ in range(world)]
     dist.all_gather(gathered, acc)
     identical = all(torch.equal(g.view(torch.int32), gathered[0].view(torch.int32)) for g in gathered)
@@ -560,8 +567,8 @@ def dp_parity_check(rank, world):
     cnt_equal = bool(torch.equal(acc[n:n + grid.Npix + 3], acc1[n:n + grid.Npix + 3])) and float(acc[n + grid.Npix + 4]) == B * world
     rel = float((acc[:n] - acc1[:n]).abs().max() / acc1[:n].abs().max())
     rel_nll = abs(float(acc[n + grid.Npix + 3]) - float(acc1[n + grid.Npix + 3])) / abs(float(acc1[n + grid.Npix + 3]))
-    ok = identical and cnt_equal and rel < 1e-4 and rel_nll < 1e-5
-    return {"ok": bool(ok), "bit_identical_across_ranks": bool(identical), "counts_equal_single_rank": cnt_equal,
+    ok = identical and cnt_equal and rel < 1e-4 and rel_nll < 1e-5 and vs_nccl < 1e-5
+    return {"ok": bool(ok), "allreduce": m.allreduce_kind, "vs_nccl_all_reduce_max_rel": vs_nccl, "bit_identical_across_ranks": bool(identical), "counts_equal_single_rank": cnt_equal,
             "grad_sums_vs_single_rank_max_rel": rel, "nll_sum_vs_single_rank_rel": rel_nll,
             "global_batch": B * world, "note": "dp_parity: ok" if ok else "dp_parity: FAILED"}
 
@@ -620,7 +627,8 @@ def main():
                 "config": main_res["config"], "clocks": main_res["clocks"], "gpu_launches": main_res["gpu_launches"],
                 "gpu_launches_how": main_res["gpu_launches_how"], "roofline": main_res["roofline"], "numa": numa}
         if world > 1:
-            line["scaling_note"] = ("headline at N > 1 is the data-parallel train step (one NCCL all-reduce per step); its N = 1 "
+            line["scaling_note"] = ("headline at N > 1 is the data-parallel train step (one all-reduce of the accumulator per step: "
+                                    "dp_parity.allreduce says which kernel); its N = 1 "
                                     "value is also.sdss_train.value of the N = 1 line, NOT that line's predict headline")
             line["dp_parity"] = dp
         for k in ("e2e", "cpu_baseline"):
@@ -630,8 +638,17 @@ def main():
             line["also"] = also
         emit(line)
     if world > 1:
+        import gc
+        import threading
         import torch.distributed as dist
+        # the line is out; tear the process group down, but never let a stuck communicator teardown hang the run
+        gc.collect()
+        torch.cuda.synchronize()
+        t = threading.Timer(30.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
         dist.destroy_process_group()
+        t.cancel()
 
 
 if __name__ == "__main__":

@@ -233,6 +233,23 @@ int qfa_ood_select(const float* nll, int B, float threshold, int k, int thr_cap,
 int qfa_sample_posterior(const QfaModel* model, const float* hmean, const float* hcov, int B, int S,
                          unsigned long long seed, float* z_out, float* h_out, float* cont_out, void* stream);
 
+/*
+ * One-shot all-reduce(sum) of the accumulator over PEER-MAPPED device memory -- the exchange step of the data-parallel
+ * train step (the reference sums over spectra at model.py:98-103; 8(f) row 4), in place of ncclAllReduce
+ * for this 80-140 KB, latency-bound message.  Every rank calls it once per step, in the same order, with
+ *   acc            n elements (float; double if precision == QFA_PREC_FP64), 16-byte aligned, summed IN PLACE
+ *   peer_base_dev  DEVICE array of `world` pointers: entry q = the peer buffer of rank q as mapped in THIS process
+ *                  (qfa_peer_buffer_bytes(n, precision, world) bytes each, zero-filled on every rank before the first call;
+ *                  e.g. one torch.distributed._symmetric_memory allocation and its buffer_ptrs_dev)
+ *   state_dev      two zero-initialised 32-bit words of LOCAL device memory (step counter, CTA ticket)
+ * One kernel: publish acc in the own peer buffer, raise a flag in every peer's, wait for every peer's flag, sum the
+ * world's buffers out of peer memory in rank order (the same bits on every rank).  No host argument changes between
+ * steps, so the call can sit inside a captured CUDA graph.  A peer that never arrives traps the kernel after 30 s.
+ */
+size_t qfa_peer_buffer_bytes(long long n, int precision, int world);
+int qfa_peer_allreduce(void* acc, long long n, int precision, void* const* peer_base_dev,
+                       unsigned int* state_dev, int world, int rank, void* stream);
+
 /* Number of kernel launches this library has issued in this process (what bench.py reports as gpu_launches). */
 unsigned long long qfa_launch_count(void);
 

@@ -90,6 +90,8 @@ SIGNATURES = {
     "qfa_mean_spectrum_sums": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP, _VP]),
     "qfa_ood_select": (_I, [_VP, _I, _F, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "qfa_sample_posterior": (_I, [_MP, _VP, _VP, _I, _I, _ULL, _VP, _VP, _VP, _VP]),
+    "qfa_peer_buffer_bytes": (_SZ, [_LL, _I, _I]),
+    "qfa_peer_allreduce": (_I, [_VP, _LL, _I, _VP, _VP, _I, _I, _VP]),
     "qfa_launch_count": (_ULL, []),
 }
 # include/qfa_b200_debug.h: hardware self-tests, design micro-benchmarks, trace hooks (not reference-facing)

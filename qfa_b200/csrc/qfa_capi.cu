@@ -16,6 +16,7 @@
 #include "qfa_tc_gram32.cuh"
 #include "qfa_tc_gram32c.cuh"
 #include "qfa_tc_gram_x3.cuh"
+#include "qfa_peer.cuh"
 
 using namespace qfa;
 
@@ -1017,6 +1018,35 @@ extern "C" int qfa_adam_clip_step_dev(float* params, float* m, float* v, const v
     if (!hyper_dev) return fail(QFA_ERR_NULL, "hyper_dev is NULL");
     return adam_launch(params, m, v, acc, nullptr, Nb, Nr, Nh, precision, 0.f, b1, b2, eps, weight_decay, 1.f, 1.f,
                        min_value, max_value, hyper_dev, loss_sum_dev, loss_scale, cursor_dev, cursor_step, stream);
+}
+
+// ---- one-shot all-reduce of `acc` over peer-mapped memory (qfa_peer.cuh): the exchange step of the data-parallel train step
+extern "C" size_t qfa_peer_buffer_bytes(long long n, int precision, int world) {
+    if (n <= 0 || world < 1 || world > peer::kMaxWorld) return 0;
+    const size_t elem = precision == QFA_PREC_FP64 ? 8 : 4;
+    return peer::kFlagBytes + 2 * peer::pub_bytes((size_t)n, elem);
+}
+
+extern "C" int qfa_peer_allreduce(void* acc, long long n, int precision, void* const* peer_base_dev, unsigned int* state_dev,
+                                  int world, int rank, void* stream) {
+    if (!acc || !peer_base_dev || !state_dev) return fail(QFA_ERR_NULL, "acc/peer_base_dev/state_dev is NULL");
+    if (n <= 0) return fail(QFA_ERR_SHAPE, "bad accumulator length %lld", n);
+    if (world < 1 || world > peer::kMaxWorld || rank < 0 || rank >= world)
+        return fail(QFA_ERR_SHAPE, "bad world=%d rank=%d (1..%d ranks)", world, rank, peer::kMaxWorld);
+    if (((uintptr_t)acc & 15u) || ((uintptr_t)peer_base_dev & 7u) || ((uintptr_t)state_dev & 7u))
+        return fail(QFA_ERR_ALIGN, "acc must be 16-byte aligned (peer_base_dev, state_dev: 8)");
+    const bool f64 = precision == QFA_PREC_FP64;
+    const size_t nvec = (size_t)n / (f64 ? 2 : 4);
+    int blocks = (int)((nvec + 255) / 256);
+    if (blocks < 1) blocks = 1;
+    if (blocks > num_sms()) blocks = num_sms();              // CTAs spin on the peers' flags: all of them must be resident
+    cudaStream_t st = (cudaStream_t)stream;
+    char* const* pb = reinterpret_cast<char* const*>(peer_base_dev);
+    if (f64) peer::k_peer_allreduce<double><<<blocks, 256, 0, st>>>((double*)acc, (size_t)n, pb, state_dev, world, rank);
+    else peer::k_peer_allreduce<float><<<blocks, 256, 0, st>>>((float*)acc, (size_t)n, pb, state_dev, world, rank);
+    QFA_LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int qfa_clip(float* params, int Nb, int Nr, int Nh, float min_value, float max_value, void* stream) {

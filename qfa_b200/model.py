@@ -82,6 +82,8 @@ class QFA(object):
         self._loss = None
         self.process_group = None  # set by enable_data_parallel()
         self._dp = False
+        self._peer = None
+        self.allreduce_kind = "none (one rank)"
         self.solve_fp64 = False    # mixed mode, 8 < Nh <= 32: per-spectrum Cholesky in double instead of float
         self.use_cuda_graph = True  # train(): replay the whole step as ONE captured CUDA graph when the loader allows it
         self._graph = None
@@ -223,18 +225,67 @@ class QFA(object):
         return x, error, zabs, mask, B
 
     # ------------------------------------------------------------------ data parallel
-    def enable_data_parallel(self, process_group=None):
-        """Shard spectra over ranks (one process per GPU); `acc` is all-reduced before the division."""
+    def enable_data_parallel(self, process_group=None, peer_allreduce=True):
+        """Shard spectra over ranks (one process per GPU); `acc` is all-reduced before the division.
+        peer_allreduce: on CUDA, sum `acc` with the library's ONE-SHOT kernel over peer-mapped memory (qfa_peer_allreduce:
+        every rank publishes its accumulator in torch symmetric memory, flags its peers over NVLink and sums the world's
+        buffers in rank order -- 8(f) row 4) instead of ncclAllReduce.  If peer memory cannot be set up on every rank the
+        step keeps NCCL; `self.allreduce_kind` says which one runs and why."""
         import torch.distributed as dist
         if not dist.is_initialized():
             raise QfaError("torch.distributed is not initialised")
         self.process_group = process_group
         self._dp = dist.get_world_size(process_group) > 1
+        self._peer = None
+        self._graph = None
+        self.allreduce_kind = "torch.distributed all_reduce" if self._dp else "none (one rank)"
+        if self._dp and peer_allreduce and self.device.type == "cuda":
+            self._setup_peer_allreduce()
+
+    def _setup_peer_allreduce(self):
+        import torch.distributed as dist
+        L = _lib.lib()
+        group = self.process_group if self.process_group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n = int(L.qfa_acc_len(self.Nb, self.Nr, self.Nh))
+        peer, why = None, ""
+        try:
+            nbytes = int(L.qfa_peer_buffer_bytes(n, PRECISIONS["fp64"], world))      # sized for a double accumulator
+            if nbytes == 0:
+                raise QfaError(f"world size {world} not supported by qfa_peer_allreduce")
+            import torch.distributed._symmetric_memory as symm
+            with self._on_device():
+                buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+                hdl = symm.rendezvous(buf, group)
+                buf.zero_()
+                state = torch.zeros(2, dtype=torch.int32, device=self.device)
+                torch.cuda.synchronize(self.device)
+            peer = dict(buf=buf, hdl=hdl, base_dev=int(hdl.buffer_ptrs_dev), state=state, world=world, rank=rank, n=n)
+        except Exception as e:                                   # no peer access, no symmetric-memory support, ...
+            why = f"{type(e).__name__}: {e}"
+        # every rank must take the same path; the reduction is also the barrier behind the zero fill of the flags
+        ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 1:
+            self._peer = peer
+            self.allreduce_kind = "qfa_peer_allreduce (one-shot over symmetric memory)"
+        else:
+            self.allreduce_kind = "nccl all_reduce (peer memory unavailable: %s)" % (why or "on another rank")
 
     def _allreduce(self, acc):
-        if self._dp:
-            import torch.distributed as dist
-            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.process_group)
+        if not self._dp:
+            return
+        if self._peer is not None and acc.is_cuda:
+            p = self._peer
+            if acc.numel() != p["n"]:
+                raise QfaError(f"accumulator of {acc.numel()} elements, peer buffers were sized for {p['n']}")
+            prec = PRECISIONS["fp64"] if acc.dtype == torch.float64 else PRECISIONS["fp32"]
+            with self._on_device():
+                _lib.check(_lib.lib().qfa_peer_allreduce(_ptr(acc), acc.numel(), prec, p["base_dev"], _ptr(p["state"]),
+                                                         p["world"], p["rank"], self._stream()), "qfa_peer_allreduce")
+            return
+        import torch.distributed as dist
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.process_group)
 
     # ------------------------------------------------------------------ hot path
     def accumulate(self, delta, error, zabs, mask, zero=True, nll_out=None):

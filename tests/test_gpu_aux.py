@@ -190,3 +190,16 @@ def test_model_on_a_non_current_device():
             assert abs(float(loss) - float(ref["loss"])) < 2e-3 * abs(float(ref["loss"]))
             outs.append(o["cont"].cpu())
     assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
+
+
+@pytest.mark.gpu
+def test_peer_allreduce_protocol_one_device():
+    """qfa_peer_allreduce (the exchange step of 8(e)): 1, 2, 3 and 8 emulated ranks on one GPU -- separate
+    buffers, states and streams, kernels that really wait for each other's flags -- float and double, vector body and scalar
+    tail, a rank enqueued a step ahead (double-buffered publish).  Bit-exact against the rank-ordered torch sum.  Own
+    process: see tests/workers/peer_one_device.py."""
+    import subprocess
+    import sys
+    w = os.path.join(os.path.dirname(os.path.abspath(__file__)), "workers", "peer_one_device.py")
+    r = subprocess.run([sys.executable, w], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PEER-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
