@@ -51,6 +51,14 @@ def test_host_side_entry_points_without_gpu():
     assert L.qfa_debug_set_trace(None) == -8
     assert L.qfa_launch_count() == 0
     assert L.qfa_ood_select(None, 0, 0.0, 4096, 0, None, None, None, None, None) == -8
+    # peer all-reduce: buffer = 128 B of flags + two 16-byte-rounded copies of the accumulator; argument errors before any launch
+    n = L.qfa_acc_len(720, 1193, 8)
+    assert L.qfa_peer_buffer_bytes(n, 1, 8) == 128 + 2 * ((4 * n + 15) // 16 * 16)
+    assert L.qfa_peer_buffer_bytes(n, 0, 8) == 128 + 2 * ((8 * n + 15) // 16 * 16)          # QFA_PREC_FP64: double accumulator
+    assert L.qfa_peer_buffer_bytes(n, 1, 33) == 0 and L.qfa_peer_buffer_bytes(0, 1, 2) == 0
+    assert L.qfa_peer_allreduce(None, n, 1, None, None, 2, 0, None) == -1
+    assert L.qfa_peer_allreduce(ctypes.c_void_p(16), n, 1, ctypes.c_void_p(16), ctypes.c_void_p(16), 2, 2, None) == -2
+    assert L.qfa_peer_allreduce(ctypes.c_void_p(20), n, 1, ctypes.c_void_p(16), ctypes.c_void_p(16), 2, 0, None) == -6
 
 
 def test_library_is_sm100a_only():

@@ -218,6 +218,8 @@ def _dp_worker(rank, world, port, q):
         m = QFA(grid.Nb, grid.Nr, 4, cpu, model_params=Pn)
         m.enable_data_parallel()
         assert m._dp
+        # the peer-memory kernel is a CUDA path: a CPU model keeps the torch.distributed collective, and says so
+        assert m._peer is None and m.allreduce_kind == "torch.distributed all_reduce"
         ld = synth.SyntheticLoader(data, mu, batch_size=24, rank=rank, world=world, seed=3, shuffle=False)
         ld.rewind()
         d, e, z, k = ld.next_batch()                     # this rank's half of the global batch
