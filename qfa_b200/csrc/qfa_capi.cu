@@ -1089,9 +1089,16 @@ static int gather_prepare(const float* flux, const float* error, const uint8_t* 
     a.perm = reinterpret_cast<const int64_t*>(perm); a.cursor = reinterpret_cast<const int64_t*>(cursor);
     a.B = B; a.Nb = Nb; a.P = Nb + Nr; a.max_series = aux::kNSeries; a.lw = aux_law(tau_law);
     a.zabs_out = zabs_out; a.delta_out = delta_out; a.error_out = error_out; a.mask_out = mask_out;
-    int grid = 8 * num_sms();                       // 8 CTAs of 256 threads per SM, each streaming whole rows
+    // CTAs of 256 threads, each streaming whole rows.  With >= 4 rows per CTA the kernel builds the separable optical-depth
+    // tables in shared memory (3 Nb floats) and runs one resident wave (6 CTAs per SM at 40 registers); smaller batches keep the
+    // direct evaluation -- building the tables costs a CTA about as much as one row (batch 500: 18.5 vs 31 us).
+    const size_t tab = 3 * (size_t)Nb * sizeof(float);
+    const bool table = tab <= 48 * 1024 && (long long)B >= 4LL * 6 * num_sms();
+    int grid = (table ? 6 : 8) * num_sms();
     if (grid > B) grid = B;
-    aux::k_gather_prepare<<<grid, 256, 0, (cudaStream_t)stream>>>(a); QFA_LAUNCHED();
+    if (table) aux::k_gather_prepare<true><<<grid, 256, tab, (cudaStream_t)stream>>>(a);
+    else aux::k_gather_prepare<false><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;
 }

@@ -37,6 +37,34 @@ def test_gather_prepare_and_mean_spectrum_match_reference_golden(name):
     assert np.array_equal(m.cpu().numpy(), g["mask"]) and np.array_equal(e.cpu().numpy(), g["error"])
 
 
+def test_gather_prepare_separable_table_path_matches_direct_path():
+    """Batches of >= 4 rows per CTA take k_gather_prepare<TABLE>: tau_total = (1 + zq)^be T1[i] + T0[i] with per-pixel tables in
+    shared memory instead of a powf per cell and line.  Same data through the table path (one batch of 3 700 rows) and the
+    direct path (batches of 925, itself pinned to the reference's goldens above), on the DESI-shaped grid whose bluest pixels
+    lie below Ly-beta .. Ly-5 (multi-line sums): delta within a few ulp of the continuum, zabs to 3e-7, error / mask exact."""
+    from qfa_b200 import DeviceDataloader, synth
+    dev = _dev()
+    grid = synth.GRIDS["desi"]
+    P, mu = synth.smooth_random_params(grid, 4, seed=3)
+    n = 3700
+    d = synth.make_spectra(P, mu, grid, n, seed=21, device=dev)
+    outs = {}
+    for bs in (n, 925):
+        dl = DeviceDataloader(d["flux"], d["error"], d["zqso"], d["mask"], grid.wav(), batch_size=bs, device=dev, shuffle=False)
+        dl.rewind()
+        parts = []
+        while dl.have_next_batch():
+            parts.append([t.clone() for t in dl.next_batch()])
+        outs[bs] = [torch.cat([p[j] for p in parts]) for j in range(4)]
+        mu_dev = dl._mu_dev
+    (d1, e1, z1, m1), (d0, e0, z0, m0) = outs[n], outs[925]
+    assert torch.equal(e1, e0) and torch.equal(m1, m0)
+    assert float((z1 - z0).abs().max() / z0.abs().max()) < 3e-7
+    rel = (d1 - d0).abs() / mu_dev.abs().clamp_min(1e-3)[None, :]
+    assert float(rel[m0].max()) < 3e-6                   # unmasked pixels (masked ones hold flux = -999: one ulp there is 6e-5)
+    assert float((d1 - d0).abs()[m0].max()) > 0.0        # really two different code paths
+
+
 def test_device_shuffle_visits_every_spectrum_once():
     from qfa_b200 import DeviceDataloader
     dev = _dev()
