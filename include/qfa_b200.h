@@ -244,7 +244,8 @@ int qfa_sample_posterior(const QfaModel* model, const float* hmean, const float*
  *   state_dev      two zero-initialised 32-bit words of LOCAL device memory (step counter, CTA ticket)
  * One kernel: publish acc in the own peer buffer, raise a flag in every peer's, wait for every peer's flag, sum the
  * world's buffers out of peer memory in rank order (the same bits on every rank).  No host argument changes between
- * steps, so the call can sit inside a captured CUDA graph.  A peer that never arrives traps the kernel after 30 s.
+ * steps, so the call can sit inside a captured CUDA graph.  A peer that has not arrived after QFA_PEER_TIMEOUT_S seconds
+ * (environment, default 600) traps the kernel.
  */
 size_t qfa_peer_buffer_bytes(long long n, int precision, int world);
 int qfa_peer_allreduce(void* acc, long long n, int precision, void* const* peer_base_dev,

@@ -1042,8 +1042,11 @@ extern "C" int qfa_peer_allreduce(void* acc, long long n, int precision, void* c
     if (blocks > num_sms()) blocks = num_sms();              // CTAs spin on the peers' flags: all of them must be resident
     cudaStream_t st = (cudaStream_t)stream;
     char* const* pb = reinterpret_cast<char* const*>(peer_base_dev);
-    if (f64) peer::k_peer_allreduce<double><<<blocks, 256, 0, st>>>((double*)acc, (size_t)n, pb, state_dev, world, rank);
-    else peer::k_peer_allreduce<float><<<blocks, 256, 0, st>>>((float*)acc, (size_t)n, pb, state_dev, world, rank);
+    static long long timeout_s = -1;
+    if (timeout_s < 0) { const char* e = getenv("QFA_PEER_TIMEOUT_S"); timeout_s = e && atoll(e) > 0 ? atoll(e) : 600; }
+    const unsigned long long tns = (unsigned long long)timeout_s * 1000000000ull;
+    if (f64) peer::k_peer_allreduce<double><<<blocks, 256, 0, st>>>((double*)acc, (size_t)n, pb, state_dev, world, rank, tns);
+    else peer::k_peer_allreduce<float><<<blocks, 256, 0, st>>>((float*)acc, (size_t)n, pb, state_dev, world, rank, tns);
     QFA_LAUNCHED();
     CK(cudaGetLastError());
     return 0;

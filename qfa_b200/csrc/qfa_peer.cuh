@@ -16,8 +16,9 @@
 //                  train step replays without host arguments.
 //
 // The grid is at most one CTA per SM (all co-resident: CTAs spin on flags), phase 1 (publish) and phase 2 (sum) are separated by a
-// ticket: the last CTA to finish publishing raises the flags.  A peer that never arrives traps the kernel after 30 s instead of
-// hanging the process.
+// ticket: the last CTA to finish publishing raises the flags.  A rank may wait for a slow peer (one that writes a checkpoint,
+// say) for as long as NCCL's watchdog would: the wait backs off with nanosleep and only traps after QFA_PEER_TIMEOUT_S seconds
+// (default 600) instead of hanging the process for ever.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -74,7 +75,8 @@ __host__ __device__ constexpr size_t pub_bytes(size_t n, size_t elem) { return (
 // acc (n elements, 16-byte aligned) <- sum over ranks of acc, in rank order.  peer_base[q] = rank q's peer buffer as mapped HERE.
 template <typename T>
 __global__ void __launch_bounds__(256) k_peer_allreduce(T* __restrict__ acc, size_t n, char* const* __restrict__ peer_base,
-                                                        unsigned* __restrict__ state, int world, int rank) {
+                                                        unsigned* __restrict__ state, int world, int rank,
+                                                        unsigned long long timeout_ns) {
     constexpr int VN = Vec16<T>::N;
     __shared__ int s_last;
     const size_t pb = pub_bytes(n, sizeof(T));
@@ -115,10 +117,10 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(T* __restrict__ acc, siz
         int spins = 0;
         while ((int)(ld_acquire_sys(f) - (s + 1u)) < 0) {
             if (++spins > 64) {
-                __nanosleep(64);
+                __nanosleep(spins > 4096 ? 1000 : 64);
                 const unsigned long long t = globaltimer_ns();
                 if (t0 == 0ull) t0 = t;
-                else if (t - t0 > 30000000000ull) __trap();           // a peer never arrived
+                else if (t - t0 > timeout_ns) __trap();               // a peer never arrived
             }
         }
     }

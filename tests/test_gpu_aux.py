@@ -229,5 +229,6 @@ def test_peer_allreduce_protocol_one_device():
     import subprocess
     import sys
     w = os.path.join(os.path.dirname(os.path.abspath(__file__)), "workers", "peer_one_device.py")
-    r = subprocess.run([sys.executable, w], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, w], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, QFA_PEER_TIMEOUT_S="30"))
     assert r.returncode == 0 and "PEER-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

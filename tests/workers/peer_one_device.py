@@ -1,6 +1,7 @@
 """qfa_peer_allreduce protocol check on ONE device: `world` ranks are emulated by `world` buffers and streams of the same GPU
 (their kernels run concurrently and really wait for each other's flags).  Run in a process of its own by
-tests/test_gpu_aux.py: a protocol bug ends in the kernel's 30 s trap, which would take the caller's CUDA context with it.
+tests/test_gpu_aux.py (with QFA_PEER_TIMEOUT_S=30): a protocol bug ends in the kernel's trap, which would take the caller's
+CUDA context with it.
 Prints PEER-OK on success."""
 import ctypes
 import os
