@@ -349,7 +349,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "spectra/sec", "value": cb["value"], "unit": "spectra/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(name, args.spectra or w["nspec"], args.precision, max(1, args.gpus)),
+            "config": dict(workload_config(name, args.spectra or w["nspec"], args.precision, max(1, args.gpus)),
+                           **({"allreduce": "none (the CPU reference is one host process: no exchange step)"}
+                              if args.gpus > 1 and w["kind"] in ("train", "graph_train") else {})),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)

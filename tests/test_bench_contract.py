@@ -40,6 +40,7 @@ def test_reference_arm_follows_the_headline_workload_of_the_gpu_arm():
     assert r.returncode == 0, r.stderr
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["config"]["workload"] == "sdss_train" and d["config"]["kind"] == "train" and d["n_gpus"] == 2
+    assert d["config"]["allreduce"].startswith("none")          # same key set as the GPU arm's N > 1 config
     assert d["value"] > 0
 
 
