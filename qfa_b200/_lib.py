@@ -51,8 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    extra = ["-DQFA_ENABLE_TRACE"] if os.environ.get("QFA_ENABLE_TRACE") else []     # clock64 stamps for scratch/*_trace.py
-    extra += os.environ.get("QFA_NVCC_EXTRA", "").split()                            # A/B variants (scratch/run_variants.sh)
+    extra = ["-DQFA_ENABLE_TRACE"] if os.environ.get("QFA_ENABLE_TRACE") else []     # clock64 stamps (include/qfa_b200_debug.h)
+    extra += os.environ.get("QFA_NVCC_EXTRA", "").split()                            # A/B variants (scripts/ab_variants.sh)
     cmd = [nvcc] + NVCC_FLAGS + extra + SOURCES + ["-o", LIB_PATH + ".tmp"]
     if verbose:
         print(" ".join(cmd))
