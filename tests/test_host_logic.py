@@ -296,3 +296,43 @@ def test_device_dataloader_matches_reference_formulas():
     while ld.have_next_batch():
         cnt += ld.next_batch()[0].shape[0]
     assert cnt == n
+
+
+def test_separable_optical_depth_identity_of_the_gather_kernel():
+    """k_gather_prepare<TABLE> (csrc/qfa_aux.cuh) evaluates  tau_total(i, row) = (1 + zq)^be * T1[i] + T0[i]  with per-pixel tables
+    T1[i] = t0 * sum_s c_s (wav_i / (lambda_s zn))^be,  T0[i] = C * sum_s c_s  over the Lyman lines redward of pixel i.  Pinned here
+    on the CPU: (a) the identity against tau_total (utils.py:174-203 of the reference, restated in qfa_b200/utils.py and itself pinned
+    to the reference's output by tests/golden/prep_*.npz) in float64, all four laws, a DESI-like grid whose bluest pixels lie
+    below the Lyman limit; (b) the same two formulas in float32 arithmetic, as the kernels evaluate them, agree to a few ulp of
+    exp(-tau) -- the bound the GPU test asserts between the table and the direct kernel."""
+    from qfa_b200.utils import LAW_CONSTANTS, _LYMAN, series_coeff, tau_total
+    wav = 910.0 * 10 ** (5.62e-5 * np.arange(2238))
+    zq = np.array([2.0, 2.7, 3.5])
+    lam = np.array([l for _, l in _LYMAN])
+    coef = np.array([series_coeff(s + 1) for s in range(len(_LYMAN))])
+    for which, (t0, be, C, zn) in LAW_CONSTANTS.items():
+        ref = tau_total(wav, zq, which=which)                                   # (3, Nb)
+        nb = ref.shape[1]
+        red = wav[:nb, None] < lam[None, :]                                      # lines redward of each pixel
+        T1 = t0 * np.sum(np.where(red, coef[None, :] * (wav[:nb, None] / (lam[None, :] * zn)) ** be, 0.0), axis=1)
+        T0 = C * np.sum(np.where(red, coef[None, :], 0.0), axis=1)
+        sep = (1.0 + zq)[:, None] ** be * T1[None, :] + T0[None, :]
+        assert np.abs(sep - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), which
+        # float32, in the kernels' order of operations
+        f = np.float32
+        w32, l32, c32 = wav[:nb].astype(f), lam.astype(f), coef.astype(f)
+        direct = np.zeros((len(zq), nb), f)
+        t1 = np.zeros(nb, f); t0s = np.zeros(nb, f)
+        for s in range(len(lam)):
+            on = w32 < l32[s]
+            if not on.any():
+                break
+            for r, z in enumerate(zq):
+                z1 = f(1.0 + z) * w32 / l32[s]
+                direct[r] += np.where(on, (f(t0) * np.power(z1 / f(zn), f(be)) + f(C)) * c32[s], f(0))
+            t1 += np.where(on, c32[s] * np.power(w32 / (l32[s] * f(zn)), f(be)), f(0))
+            t0s += np.where(on, c32[s], f(0))
+        for r, z in enumerate(zq):
+            g = np.power(f(1.0 + z), f(be))
+            table = g * (f(t0) * t1) + f(C) * t0s
+            assert np.abs(np.exp(-table) - np.exp(-direct[r])).max() < 1e-6, (which, z)
